@@ -1,0 +1,498 @@
+// C ABI of the B200-native evacuation environment (see include/evac_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Host side: handle + launch plumbing only; all
+// arithmetic lives in evac_kernels.cuh.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/evac_b200.h"
+#include "evac_kernels.cuh"
+
+using namespace evac;
+
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return fail(EVAC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct EvacHandle {
+  EvacConfig cfg;
+  int E, N, device, obs_dim, prec;
+  uint64_t seed;
+  long long env_offset;
+  // device state
+  void* pos = nullptr;
+  void* dir = nullptr;
+  uint8_t* status = nullptr;
+  float2* agent_pos = nullptr;
+  float2* agent_dir = nullptr;
+  int* now = nullptr;
+  int* episode = nullptr;
+  long long* overall = nullptr;
+  double* acc = nullptr;
+  float* ep_stats = nullptr;
+  uint8_t* ep_finished = nullptr;
+  double* totals = nullptr;
+  // staging for the *_host entry points
+  cudaStream_t stream = nullptr;
+  float *h_actions = nullptr, *h_noise = nullptr, *h_obs = nullptr, *h_reward = nullptr;
+  uint8_t *h_term = nullptr, *h_trunc = nullptr;
+  float *d_actions = nullptr, *d_noise = nullptr, *d_obs = nullptr, *d_reward = nullptr;
+  uint8_t *d_term = nullptr, *d_trunc = nullptr;
+  int64_t launches = 0;
+  int threads = 0, ppt = 0;
+  int num_sms = 0;
+};
+
+// smallest double b such that sqrt(v) >= t for every v >= b  <=>  (v < b) == (sqrt(v) < t)
+static double sq_boundary(double t) {
+  double v = t * t;
+  while (v > 0 && sqrt(nextafter(v, 0.0)) >= t) v = nextafter(v, 0.0);
+  while (sqrt(v) < t) v = nextafter(v, INFINITY);
+  return v;
+}
+static float round_up_f32(double b) {
+  float f = (float)b;
+  if ((double)f < b) f = nextafterf(f, INFINITY);
+  return f;
+}
+template <typename real> static real thr2_of(double t);
+template <> float thr2_of<float>(double t) { return round_up_f32(sq_boundary(t)); }
+template <> double thr2_of<double>(double t) { return sq_boundary(t); }
+
+static int compute_obs_dim(const EvacConfig& c) {
+  const int n = c.number_of_pedestrians;
+  if (c.positions == EVAC_POS_GRAV) return 6;
+  const int sc = c.statuses == EVAC_STAT_OHE ? 4 : (c.statuses == EVAC_STAT_CAT ? 1 : 0);
+  if (c.obs_type == EVAC_OBS_BOX) return (n + 2) * (2 + sc);
+  return 4 + 2 * n + sc * n;
+}
+
+template <typename real>
+static KArgs<real> make_args(const EvacHandle* h) {
+  const EvacConfig& c = h->cfg;
+  KArgs<real> a;
+  memset(&a, 0, sizeof(a));
+  a.E = h->E; a.N = h->N; a.obs_dim = h->obs_dim;
+  a.width = (real)c.width; a.height = (real)c.height; a.step_size = (real)c.step_size; a.noise_coef = (real)c.noise_coef;
+  a.enslaving = (real)c.enslaving_degree; a.one_minus_enslaving = (real)(1.0 - c.enslaving_degree);
+  a.width_f = (float)c.width; a.height_f = (float)c.height; a.step_size_f = (float)c.step_size;
+  a.eps_f = (float)c.eps; a.enslaving_f = (float)c.enslaving_degree;
+  a.thr2_ped = thr2_of<real>(c.to_pedestrian); a.thr2_leader = thr2_of<real>(c.to_leader);
+  a.thr2_exit = thr2_of<real>(c.to_exit); a.thr2_escape = thr2_of<real>(c.to_escape);
+  a.exit_reward = c.is_new_exiting_reward; a.follow_reward = c.is_new_followers_reward;
+  a.term_wall = c.is_termination_agent_wall_collision;
+  a.init_reward = (real)c.init_reward_each_step; a.intrinsic_coef = (real)c.intrinsic_reward_coef;
+  a.max_timesteps = c.max_timesteps;
+  a.positions = c.positions; a.statuses = c.statuses; a.obs_type = c.obs_type;
+  a.alpha = (real)c.alpha; a.eps = (real)c.eps;
+  const double ap2 = c.alpha + 2.0;
+  a.alpha_plus2_int = (ap2 == floor(ap2) && ap2 >= 1.0 && ap2 <= 64.0) ? (int)ap2 : 0;
+  a.auto_reset = c.auto_reset;
+  a.pos = reinterpret_cast<typename vec2<real>::type*>(h->pos);
+  a.dir = reinterpret_cast<typename vec2<real>::type*>(h->dir);
+  a.status = h->status; a.agent_pos = h->agent_pos; a.agent_dir = h->agent_dir;
+  a.now = h->now; a.episode = h->episode; a.overall = h->overall; a.acc = h->acc;
+  a.ep_stats = h->ep_stats; a.ep_finished = h->ep_finished; a.totals = h->totals;
+  a.seed = h->seed; a.env_offset = h->env_offset;
+  a.num_steps = 1; a.agent_kind = AGENT_TABLE;
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename real, int THREADS, int PPT>
+static int launch_step_t(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
+  const size_t smem = Tile<real>::bytes(THREADS * PPT);
+  static thread_local bool attr_set[16] = {false};
+  auto kern = evac_step_kernel<real, THREADS, PPT>;
+  if (smem > 48 * 1024 && !attr_set[h->device & 15]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[h->device & 15] = true;
+  }
+  kern<<<a.E, THREADS, smem, st>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return EVAC_OK;
+}
+
+static void pick_shape(int n, int* threads, int* ppt) {
+  if (n <= 64) { *threads = 64; *ppt = 1; }
+  else if (n <= 128) { *threads = 128; *ppt = 1; }
+  else if (n <= 256) { *threads = 256; *ppt = 1; }
+  else if (n <= 512) { *threads = 256; *ppt = 2; }
+  else if (n <= 1024) { *threads = 512; *ppt = 2; }
+  else if (n <= 2048) { *threads = 512; *ppt = 4; }
+  else { *threads = 1024; *ppt = 4; }
+}
+
+template <typename real>
+static int launch_step(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
+  switch (h->threads * 16 + h->ppt) {
+    case 64 * 16 + 1: return launch_step_t<real, 64, 1>(h, a, st);
+    case 128 * 16 + 1: return launch_step_t<real, 128, 1>(h, a, st);
+    case 256 * 16 + 1: return launch_step_t<real, 256, 1>(h, a, st);
+    case 256 * 16 + 2: return launch_step_t<real, 256, 2>(h, a, st);
+    case 512 * 16 + 2: return launch_step_t<real, 512, 2>(h, a, st);
+    case 512 * 16 + 4: return launch_step_t<real, 512, 4>(h, a, st);
+    case 1024 * 16 + 4: return launch_step_t<real, 1024, 4>(h, a, st);
+  }
+  return fail(EVAC_ERR_INVALID, "no kernel shape for N=%d", h->N);
+}
+
+template <typename real>
+static int launch_aux(EvacHandle* h, int flags, const uint8_t* mask, float* obs, cudaStream_t st) {
+  KArgs<real> a = make_args<real>(h);
+  evac_aux_kernel<real><<<h->E, 128, 0, st>>>(a, flags, mask, obs);
+  CK(cudaGetLastError());
+  h->launches++;
+  return EVAC_OK;
+}
+
+static int set_device(const EvacHandle* h) {
+  CK(cudaSetDevice(h->device));
+  return EVAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t evac_abi_version(void) { return EVAC_ABI_VERSION; }
+const char* evac_last_error(void) { return g_err; }
+
+int evac_default_config(EvacConfig* c) {
+  if (!c) return fail(EVAC_ERR_INVALID, "cfg is NULL");
+  memset(c, 0, sizeof(*c));
+  c->abi_version = EVAC_ABI_VERSION;
+  c->number_of_pedestrians = 10;  // config.py:11
+  c->width = 1.0; c->height = 1.0; c->step_size = 0.01; c->noise_coef = 0.2; c->eps = 1e-8;
+  c->enslaving_degree = 1.0;
+  c->is_new_exiting_reward = 0; c->is_new_followers_reward = 1; c->intrinsic_reward_coef = 0.0;
+  c->is_termination_agent_wall_collision = 0; c->init_reward_each_step = -1.0; c->max_timesteps = 2000;
+  c->positions = EVAC_POS_ABS; c->statuses = EVAC_STAT_NO; c->obs_type = EVAC_OBS_DICT; c->alpha = 3.0;
+  c->to_leader = 0.2; c->to_pedestrian = 0.1; c->to_exit = 0.4; c->to_escape = 0.01;  // constants.py:35-38
+  c->auto_reset = 0; c->precision = EVAC_PREC_F32;
+  return EVAC_OK;
+}
+
+int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_t seed, int64_t env_index_offset,
+                EvacHandle** out) {
+  if (!cfg || !out) return fail(EVAC_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (cfg->abi_version != EVAC_ABI_VERSION) return fail(EVAC_ERR_INVALID, "EvacConfig.abi_version %d != %d", cfg->abi_version, EVAC_ABI_VERSION);
+  if (num_envs < 1) return fail(EVAC_ERR_INVALID, "num_envs must be >= 1");
+  if (cfg->number_of_pedestrians < 1 || cfg->number_of_pedestrians > 4096)
+    return fail(EVAC_ERR_INVALID, "number_of_pedestrians=%d outside the supported range 1..4096", cfg->number_of_pedestrians);
+  if (cfg->positions < 0 || cfg->positions > 2 || cfg->statuses < 0 || cfg->statuses > 2 || cfg->obs_type < 0 || cfg->obs_type > 1)
+    return fail(EVAC_ERR_INVALID, "invalid observation mode");  // ValueError in the reference (wrappers.py:45,75)
+  if (cfg->positions == EVAC_POS_GRAV && cfg->obs_type == EVAC_OBS_BOX)
+    return fail(EVAC_ERR_UNSUPPORTED, "positions='grav' with type='Box' is NotImplementedError in the reference (wrappers/config.py:80-81)");
+  if (cfg->precision != EVAC_PREC_F32 && cfg->precision != EVAC_PREC_F64) return fail(EVAC_ERR_INVALID, "invalid precision");
+  if (!(cfg->to_leader > 0 && cfg->to_pedestrian > 0 && cfg->to_exit > 0 && cfg->to_escape > 0))
+    return fail(EVAC_ERR_INVALID, "switch distances must be positive");
+  if (cfg->max_timesteps < 1) return fail(EVAC_ERR_INVALID, "max_timesteps must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(EVAC_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(EVAC_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(EVAC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+
+  EvacHandle* h = new (std::nothrow) EvacHandle();
+  if (!h) return fail(EVAC_ERR_INVALID, "out of host memory");
+  h->cfg = *cfg; h->E = num_envs; h->N = cfg->number_of_pedestrians; h->device = device;
+  h->obs_dim = compute_obs_dim(*cfg); h->prec = cfg->precision; h->seed = seed; h->env_offset = env_index_offset;
+  h->num_sms = prop.multiProcessorCount;
+  pick_shape(h->N, &h->threads, &h->ppt);
+  const size_t en = (size_t)h->E * h->N, es = h->prec == EVAC_PREC_F64 ? 16 : 8;
+#define ALLOC(ptr, bytes)                                                      \
+  do {                                                                         \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                      \
+    if (_e != cudaSuccess) { evac_destroy(h); return fail(EVAC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(_e)); } \
+    cudaMemset((ptr), 0, (bytes));                                             \
+  } while (0)
+  ALLOC(h->pos, en * es); ALLOC(h->dir, en * es); ALLOC(h->status, en);
+  ALLOC(h->agent_pos, (size_t)h->E * sizeof(float2)); ALLOC(h->agent_dir, (size_t)h->E * sizeof(float2));
+  ALLOC(h->now, (size_t)h->E * sizeof(int)); ALLOC(h->episode, (size_t)h->E * sizeof(int));
+  ALLOC(h->overall, (size_t)h->E * sizeof(long long)); ALLOC(h->acc, (size_t)h->E * 3 * sizeof(double));
+  ALLOC(h->ep_stats, (size_t)h->E * EVAC_NUM_EPISODE_STATS * sizeof(float)); ALLOC(h->ep_finished, (size_t)h->E);
+  ALLOC(h->totals, (1 + EVAC_NUM_EPISODE_STATS) * sizeof(double));
+#undef ALLOC
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaDeviceSynchronize());
+  *out = h;
+  return EVAC_OK;
+}
+
+int evac_destroy(EvacHandle* h) {
+  if (!h) return EVAC_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  void* dptrs[] = {h->pos, h->dir, h->status, h->agent_pos, h->agent_dir, h->now, h->episode, h->overall, h->acc,
+                   h->ep_stats, h->ep_finished, h->totals, h->d_actions, h->d_noise, h->d_obs, h->d_reward, h->d_term, h->d_trunc};
+  for (void* p : dptrs) if (p) cudaFree(p);
+  void* hptrs[] = {h->h_actions, h->h_noise, h->h_obs, h->h_reward, h->h_term, h->h_trunc};
+  for (void* p : hptrs) if (p) cudaFreeHost(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return EVAC_OK;
+}
+
+int32_t evac_obs_dim(const EvacHandle* h) { return h ? h->obs_dim : -1; }
+int32_t evac_num_envs(const EvacHandle* h) { return h ? h->E : -1; }
+int32_t evac_state_elem_size(const EvacHandle* h) { return h ? (h->prec == EVAC_PREC_F64 ? 8 : 4) : -1; }
+int64_t evac_launch_count(const EvacHandle* h) { return h ? h->launches : -1; }
+
+int evac_reset(EvacHandle* h, const uint8_t* reset_mask, float* obs, void* stream) {
+  if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
+  if (int r = set_device(h)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int flags = AUX_RESET | (obs ? AUX_OBS : 0);
+  return h->prec == EVAC_PREC_F64 ? launch_aux<double>(h, flags, reset_mask, obs, st) : launch_aux<float>(h, flags, reset_mask, obs, st);
+}
+
+int evac_observe(EvacHandle* h, float* obs, void* stream) {
+  if (!h || !obs) return fail(EVAC_ERR_INVALID, "NULL argument");
+  if (int r = set_device(h)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->prec == EVAC_PREC_F64 ? launch_aux<double>(h, AUX_OBS, nullptr, obs, st) : launch_aux<float>(h, AUX_OBS, nullptr, obs, st);
+}
+
+int evac_set_state(EvacHandle* h, const void* positions, const void* directions, const uint8_t* statuses,
+                   const float* agent_position, const float* agent_direction, const int32_t* now, void* stream) {
+  if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
+  if (int r = set_device(h)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t en = (size_t)h->E * h->N, es = h->prec == EVAC_PREC_F64 ? 16 : 8;
+  if (positions) CK(cudaMemcpyAsync(h->pos, positions, en * es, cudaMemcpyDeviceToDevice, st));
+  if (directions) CK(cudaMemcpyAsync(h->dir, directions, en * es, cudaMemcpyDeviceToDevice, st));
+  if (agent_position) CK(cudaMemcpyAsync(h->agent_pos, agent_position, (size_t)h->E * 8, cudaMemcpyDeviceToDevice, st));
+  if (agent_direction) CK(cudaMemcpyAsync(h->agent_dir, agent_direction, (size_t)h->E * 8, cudaMemcpyDeviceToDevice, st));
+  if (now) CK(cudaMemcpyAsync(h->now, now, (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
+  if (statuses) {
+    CK(cudaMemcpyAsync(h->status, statuses, en, cudaMemcpyDeviceToDevice, st));
+  } else if (positions || agent_position) {  // pedestrians.py:21-26: statuses follow from the positions
+    return h->prec == EVAC_PREC_F64 ? launch_aux<double>(h, AUX_STATUS, nullptr, nullptr, st) : launch_aux<float>(h, AUX_STATUS, nullptr, nullptr, st);
+  }
+  return EVAC_OK;
+}
+
+int evac_get_state(EvacHandle* h, void* positions, void* directions, uint8_t* statuses, float* agent_position,
+                   float* agent_direction, int32_t* now, void* stream) {
+  if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
+  if (int r = set_device(h)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t en = (size_t)h->E * h->N, es = h->prec == EVAC_PREC_F64 ? 16 : 8;
+  if (positions) CK(cudaMemcpyAsync(positions, h->pos, en * es, cudaMemcpyDeviceToDevice, st));
+  if (directions) CK(cudaMemcpyAsync(directions, h->dir, en * es, cudaMemcpyDeviceToDevice, st));
+  if (statuses) CK(cudaMemcpyAsync(statuses, h->status, en, cudaMemcpyDeviceToDevice, st));
+  if (agent_position) CK(cudaMemcpyAsync(agent_position, h->agent_pos, (size_t)h->E * 8, cudaMemcpyDeviceToDevice, st));
+  if (agent_direction) CK(cudaMemcpyAsync(agent_direction, h->agent_dir, (size_t)h->E * 8, cudaMemcpyDeviceToDevice, st));
+  if (now) CK(cudaMemcpyAsync(now, h->now, (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
+  return EVAC_OK;
+}
+
+int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const float* actions, const float* noise, float* obs,
+                 int32_t obs_every_step, float* reward_sum, uint8_t* terminated, uint8_t* truncated, void* stream) {
+  if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
+  if (num_steps < 1) return fail(EVAC_ERR_INVALID, "num_steps must be >= 1");
+  if (agent_kind < EVAC_AGENT_TABLE || agent_kind > EVAC_AGENT_ROTATING) return fail(EVAC_ERR_INVALID, "invalid agent_kind");
+  if (agent_kind == EVAC_AGENT_TABLE && !actions) return fail(EVAC_ERR_INVALID, "actions is NULL");
+  if (int r = set_device(h)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->prec == EVAC_PREC_F64) {
+    KArgs<double> a = make_args<double>(h);
+    a.actions = (const float2*)actions; a.noise = noise; a.obs = obs; a.obs_every_step = obs_every_step;
+    a.reward = reward_sum; a.terminated = terminated; a.truncated = truncated; a.num_steps = num_steps; a.agent_kind = agent_kind;
+    return launch_step<double>(h, a, st);
+  }
+  KArgs<float> a = make_args<float>(h);
+  a.actions = (const float2*)actions; a.noise = noise; a.obs = obs; a.obs_every_step = obs_every_step;
+  a.reward = reward_sum; a.terminated = terminated; a.truncated = truncated; a.num_steps = num_steps; a.agent_kind = agent_kind;
+  return launch_step<float>(h, a, st);
+}
+
+int evac_step(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward, uint8_t* terminated,
+              uint8_t* truncated, void* stream) {
+  if (!actions) return fail(EVAC_ERR_INVALID, "actions is NULL");
+  return evac_rollout(h, 1, EVAC_AGENT_TABLE, actions, noise, obs, 0, reward, terminated, truncated, stream);
+}
+
+int evac_step_host(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward, uint8_t* terminated,
+                   uint8_t* truncated) {
+  if (!h || !actions) return fail(EVAC_ERR_INVALID, "NULL argument");
+  if (int r = set_device(h)) return r;
+  const size_t E = h->E, N = h->N, D = h->obs_dim;
+  if (!h->h_actions) {
+    CK(cudaMallocHost((void**)&h->h_actions, E * 8)); CK(cudaMalloc((void**)&h->d_actions, E * 8));
+    CK(cudaMallocHost((void**)&h->h_obs, E * D * 4)); CK(cudaMalloc((void**)&h->d_obs, E * D * 4));
+    CK(cudaMallocHost((void**)&h->h_reward, E * 4)); CK(cudaMalloc((void**)&h->d_reward, E * 4));
+    CK(cudaMallocHost((void**)&h->h_term, E)); CK(cudaMalloc((void**)&h->d_term, E));
+    CK(cudaMallocHost((void**)&h->h_trunc, E)); CK(cudaMalloc((void**)&h->d_trunc, E));
+  }
+  if (noise && !h->h_noise) { CK(cudaMallocHost((void**)&h->h_noise, E * N * 4)); CK(cudaMalloc((void**)&h->d_noise, E * N * 4)); }
+  cudaStream_t st = h->stream;
+  memcpy(h->h_actions, actions, E * 8);
+  CK(cudaMemcpyAsync(h->d_actions, h->h_actions, E * 8, cudaMemcpyHostToDevice, st));
+  if (noise) { memcpy(h->h_noise, noise, E * N * 4); CK(cudaMemcpyAsync(h->d_noise, h->h_noise, E * N * 4, cudaMemcpyHostToDevice, st)); }
+  if (int r = evac_step(h, h->d_actions, noise ? h->d_noise : nullptr, obs ? h->d_obs : nullptr, h->d_reward, h->d_term, h->d_trunc, st)) return r;
+  if (obs) CK(cudaMemcpyAsync(h->h_obs, h->d_obs, E * D * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->h_reward, h->d_reward, E * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (obs) memcpy(obs, h->h_obs, E * D * 4);
+  if (reward) memcpy(reward, h->h_reward, E * 4);
+  if (terminated) memcpy(terminated, h->h_term, E);
+  if (truncated) memcpy(truncated, h->h_trunc, E);
+  return EVAC_OK;
+}
+
+int evac_episode_stats(EvacHandle* h, float* stats, uint8_t* finished, double* totals, void* stream) {
+  if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
+  if (int r = set_device(h)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stats) CK(cudaMemcpyAsync(stats, h->ep_stats, (size_t)h->E * EVAC_NUM_EPISODE_STATS * 4, cudaMemcpyDeviceToDevice, st));
+  if (finished) {
+    CK(cudaMemcpyAsync(finished, h->ep_finished, (size_t)h->E, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(h->ep_finished, 0, (size_t)h->E, st));
+  }
+  if (totals) CK(cudaMemcpyAsync(totals, h->totals, (1 + EVAC_NUM_EPISODE_STATS) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return EVAC_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Measurement probes.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) probe_fma_kernel(float* out, int iters, float seed_a, float seed_b) {
+  // 8 independent chains per thread; PACKED uses fma.rn.f32x2 (2 FMAs per instruction)
+  const float t = (float)threadIdx.x * 1e-3f;
+  if (PACKED) {
+    float2 c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = make_float2(t + k, t - k);
+    const float2 a = make_float2(seed_a, seed_a), b = make_float2(seed_b, seed_b);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = __ffma2_rn(c[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k].x + c[k].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  } else {
+    float c[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c[k] = t + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) c[k] = fmaf(c[k], seed_a, seed_b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += c[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  }
+}
+
+// Standalone launch of the SAME pairwise_pass device function the fused step kernel uses, on the same
+// CTA shape (64 threads, one pedestrian per thread, one environment per CTA).
+__global__ void __launch_bounds__(64) probe_pairwise_kernel(const float2* __restrict__ pos, const float2* __restrict__ unit,
+                                                            float2* __restrict__ out, int N, int reps, float thr2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tile<float> tile(smem_raw, 64);
+  const int tid = threadIdx.x, e = blockIdx.x;
+  float2 p = make_float2(PARK, PARK), u = make_float2(0.f, 0.f);
+  if (tid < N) { p = pos[(size_t)e * N + tid]; u = unit[(size_t)e * N + tid]; }
+  tile.put(tid, p.x, p.y, u.x, u.y);
+  __syncthreads();
+  float xi[1] = {p.x}, yi[1] = {p.y}, sx[1], sy[1], cnt[1];
+  float accx = 0.f, accy = 0.f;
+  for (int r = 0; r < reps; ++r) {
+    pairwise_pass<1, false>(tile, N, xi, yi, thr2, sx, sy, cnt);
+    accx += sx[0]; accy += sy[0];
+    xi[0] += 1e-9f * sx[0];  // data dependence between passes so they cannot be hoisted
+  }
+  if (tid < N) out[(size_t)e * N + tid] = make_float2(accx, accy);
+}
+
+extern "C" {
+
+int evac_probe_fma(int32_t device, int32_t packed, int32_t iters, float* ms, double* flops) {
+  if (!ms || !flops) return fail(EVAC_ERR_INVALID, "NULL argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  float* out = nullptr;
+  CK(cudaMalloc((void**)&out, (size_t)blocks * threads * 4));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(cudaEventRecord(e0));
+    if (packed) probe_fma_kernel<true><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f);
+    else probe_fma_kernel<false><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+  }
+  CK(cudaEventElapsedTime(ms, e0, e1));
+  *flops = (double)blocks * threads * (double)iters * 16.0 * 2.0;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  return EVAC_OK;
+}
+
+int evac_probe_pairwise(int32_t device, int32_t num_envs, int32_t n, int32_t reps, float* ms, double* pairs) {
+  if (!ms || !pairs || n < 1 || n > 64 || num_envs < 1) return fail(EVAC_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(device));
+  const size_t en = (size_t)num_envs * n;
+  float2 *pos = nullptr, *unit = nullptr, *out = nullptr;
+  CK(cudaMalloc((void**)&pos, en * 8)); CK(cudaMalloc((void**)&unit, en * 8)); CK(cudaMalloc((void**)&out, en * 8));
+  float2* hp = (float2*)malloc(en * 8);
+  float2* hu = (float2*)malloc(en * 8);
+  uint32_t s = 12345u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)(s >> 8) * (1.0f / 16777216.0f); };
+  for (size_t i = 0; i < en; ++i) {
+    hp[i] = make_float2(2.f * rnd() - 1.f, 2.f * rnd() - 1.f);
+    const float th = 6.2831853f * rnd();
+    hu[i] = make_float2(cosf(th), sinf(th));
+  }
+  CK(cudaMemcpy(pos, hp, en * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(unit, hu, en * 8, cudaMemcpyHostToDevice));
+  free(hp); free(hu);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const float thr2 = round_up_f32(sq_boundary(0.1));
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(cudaEventRecord(e0));
+    probe_pairwise_kernel<<<num_envs, 64, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(ms, e0, e1));
+  *pairs = (double)num_envs * (double)n * (double)n * (double)reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(pos); cudaFree(unit); cudaFree(out);
+  return EVAC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,705 @@
+// Fused evacuation step kernels for sm_100a (B200).
+//
+// One CTA per environment.  The CTA stages that environment's pedestrian positions and unit
+// directions in shared memory, every thread owns PPT pedestrians in registers, and ONE kernel
+// performs, per step (reference file:line in brackets, relative to the reference root):
+//   agent step + wall test                         [src/env/env/area.py:182-210]
+//   escaped / exiting preparation                  [area.py:79-90]
+//   Vicsek neighbour alignment inside the vision radius, O(N^2) pairwise pass   [area.py:93-120]
+//   additive angular noise (injected or Philox)    [area.py:124-133]
+//   leader enslaving blend                         [area.py:138-142]
+//   position integration + wall reflection         [area.py:144-152]
+//   status transitions                             [src/env/env/statuses.py:29-48]
+//   status / intrinsic rewards, termination        [src/env/env/reward.py:19-46, area.py:174-180, env.py:158-171]
+//   observation encoding (abs/rel, no/ohe/cat, Dict/Box, gravity)   [src/env/wrappers/wrappers.py:8-96,
+//                                                   src/env/wrappers/gravity_encoding.py:8-81]
+//   optional same-step auto-reset                  [pedestrians.py:16-27 semantics, gymnasium vector env]
+// and can iterate `num_steps` steps with the state resident in registers / shared memory.
+//
+// The pairwise pass uses Blackwell's packed FP32 pipe instructions (FADD2 / FMUL2 / FFMA2 via
+// __fadd2_rn / __fmul2_rn / __ffma2_rn, sm_100+ only): two neighbours j are evaluated per
+// instruction, the "is inside the vision radius" mask is folded into the data as a 0/1 float
+// (one FSET per pair) so there is no predicated control flow, and non-moving (escaped / padding)
+// slots are parked far away with a zero direction.  Nothing here is a dense contraction, so the
+// tensor cores are not used (BASELINE.json north_star).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "philox.cuh"
+
+namespace evac {
+
+constexpr int ST_NONE = 0, ST_VISCEK = 1, ST_FOLLOWER = 2, ST_EXITING = 3, ST_ESCAPED = 4;
+constexpr int POS_ABS = 0, POS_REL = 1, POS_GRAV = 2;
+constexpr int STAT_NO = 0, STAT_OHE = 1, STAT_CAT = 2;
+constexpr int OBS_DICT = 0, OBS_BOX = 1;
+constexpr int AGENT_TABLE = 0, AGENT_RANDOM = 1, AGENT_ROTATING = 2;
+constexpr int NUM_EPISODE_STATS = 9;
+constexpr float PARK = 1.0e18f;  // parking coordinate of non-moving slots: (1e18)^2*2 < FLT_MAX
+
+template <typename real> struct vec2;
+template <> struct vec2<float> { using type = float2; };
+template <> struct vec2<double> { using type = double2; };
+
+// Everything a launch needs; passed by value as a __grid_constant__.
+template <typename real>
+struct KArgs {
+  // ---- shapes
+  int E, N, obs_dim;
+  // ---- physics (EnvConfig)
+  real width, height, step_size, noise_coef, enslaving, one_minus_enslaving;
+  float width_f, height_f, step_size_f, eps_f, enslaving_f;  // the agent's arithmetic is float32 in the reference
+  // thresholds on SQUARED distances, chosen on the host so that (d2 < thr2) == (sqrt(d2) < thr) exactly
+  real thr2_ped, thr2_leader, thr2_exit, thr2_escape;
+  int exit_reward, follow_reward, term_wall;
+  real init_reward, intrinsic_coef;
+  int max_timesteps;
+  // ---- observation (EnvWrappersConfig)
+  int positions, statuses, obs_type;
+  real alpha, eps;
+  int alpha_plus2_int;  // alpha + 2 when it is a small integer, else 0 (=> pow)
+  int auto_reset;
+  // ---- persistent state (owned by the handle)
+  typename vec2<real>::type* pos;  // [E,N]
+  typename vec2<real>::type* dir;  // [E,N]
+  uint8_t* status;                 // [E,N]
+  float2* agent_pos;               // [E]
+  float2* agent_dir;               // [E]
+  int* now;                        // [E]
+  int* episode;                    // [E]   episode index (Philox counter word)
+  long long* overall;              // [E]   overall_timesteps
+  double* acc;                     // [E,3] episode_reward, episode_intrinsic_reward, episode_status_reward
+  float* ep_stats;                 // [E,9] last finished episode
+  uint8_t* ep_finished;            // [E]
+  double* totals;                  // [1+9]
+  // ---- per-call I/O
+  const float2* actions;  // [steps,E] or NULL
+  const float* noise;     // [steps,E,N] or NULL
+  float* obs;             // [E,obs_dim] or [steps,E,obs_dim]
+  int obs_every_step;
+  float* reward;          // [E]  (sum over steps)
+  uint8_t* terminated;    // [E]  (OR over steps)
+  uint8_t* truncated;     // [E]
+  int num_steps, agent_kind;
+  uint64_t seed;
+  long long env_offset;
+};
+
+// ------------------------------------------------------------------------------------------
+// small math helpers, float / double overloads
+__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float sqrt_(float x) { return __fsqrt_rn(x); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_(double a, double b) { return a / b; }
+__device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+
+template <typename real>
+__device__ __forceinline__ real ipow(real x, int n) {  // x^n, n >= 1, by squaring
+  real r = (real)1;
+  while (n) {
+    if (n & 1) r *= x;
+    x *= x;
+    n >>= 1;
+  }
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// status is a pure function of (pedestrian position, agent position)  [statuses.py:29-48]
+template <typename real>
+__device__ __forceinline__ int status_of(real px, real py, real apx, real apy, const KArgs<real>& a, real& d2_exit) {
+  const real ax = apx - px, ay = apy - py;
+  const real da2 = ax * ax + ay * ay;
+  const real ex = (real)0 - px, ey = (real)-1 - py;  // exit = (0,-1)  [area.py:36-39]
+  d2_exit = ex * ex + ey * ey;
+  int s = ST_VISCEK;
+  if (da2 < a.thr2_leader) s = ST_FOLLOWER;
+  if (d2_exit < a.thr2_exit) s = ST_EXITING;
+  if (d2_exit < a.thr2_escape) s = ST_ESCAPED;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory tile of "source" records: for slot j the position (x,y) and unit direction (ux,uy).
+//   float : two slots per float4 -> P2[j/2] = (x_j, x_j+1, y_j, y_j+1), U2[j/2] = (ux_j, ux_j+1, uy_j, uy_j+1)
+//           so one LDS.128 feeds one packed (f32x2) operand pair.
+//   double: four planar arrays.
+template <typename real>
+struct Tile;
+
+template <>
+struct Tile<float> {
+  float4* P2;
+  float4* U2;
+  __device__ __forceinline__ Tile(unsigned char* base, int slots) {
+    P2 = reinterpret_cast<float4*>(base);
+    U2 = P2 + slots / 2;
+  }
+  static __host__ __device__ constexpr size_t bytes(int slots) { return (size_t)slots * 16; }
+  __device__ __forceinline__ void put(int j, float x, float y, float ux, float uy) {
+    float* p = reinterpret_cast<float*>(P2 + (j >> 1)) + (j & 1);
+    float* u = reinterpret_cast<float*>(U2 + (j >> 1)) + (j & 1);
+    p[0] = x;
+    p[2] = y;
+    u[0] = ux;
+    u[2] = uy;
+  }
+};
+
+template <>
+struct Tile<double> {
+  double *X, *Y, *UX, *UY;
+  __device__ __forceinline__ Tile(unsigned char* base, int slots) {
+    X = reinterpret_cast<double*>(base);
+    Y = X + slots;
+    UX = Y + slots;
+    UY = UX + slots;
+  }
+  static __host__ __device__ constexpr size_t bytes(int slots) { return (size_t)slots * 32; }
+  __device__ __forceinline__ void put(int j, double x, double y, double ux, double uy) {
+    X[j] = x;
+    Y[j] = y;
+    UX[j] = ux;
+    UY[j] = uy;
+  }
+};
+
+// The pairwise neighbour-alignment pass [area.py:105-119]: for each of this thread's PPT pedestrians
+// i, sum the unit directions of all slots j with |p_i - p_j|^2 < thr2 (self included).
+// count[] (number of neighbours, area.py:108) is only produced when COUNT is set (fp64 parity mode).
+template <int PPT, bool COUNT>
+__device__ __forceinline__ void pairwise_pass(const Tile<float>& t, int nslots, const float (&xi)[PPT],
+                                              const float (&yi)[PPT], float thr2, float (&sx)[PPT], float (&sy)[PPT],
+                                              float (&cnt)[PPT]) {
+  float2 ax[PPT], ay[PPT], ac[PPT], nx[PPT], ny[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    ax[k] = make_float2(0.f, 0.f);
+    ay[k] = make_float2(0.f, 0.f);
+    ac[k] = make_float2(0.f, 0.f);
+    nx[k] = make_float2(-xi[k], -xi[k]);
+    ny[k] = make_float2(-yi[k], -yi[k]);
+  }
+  const int n2 = (nslots + 1) >> 1;
+#pragma unroll 4
+  for (int j = 0; j < n2; ++j) {
+    const float4 p = t.P2[j];  // broadcast LDS.128
+    const float4 u = t.U2[j];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const float2 dx = __fadd2_rn(make_float2(p.x, p.y), nx[k]);
+      const float2 dy = __fadd2_rn(make_float2(p.z, p.w), ny[k]);
+      float2 d2 = __fmul2_rn(dx, dx);
+      d2 = __ffma2_rn(dy, dy, d2);
+      const float2 w = make_float2(d2.x < thr2 ? 1.f : 0.f, d2.y < thr2 ? 1.f : 0.f);
+      ax[k] = __ffma2_rn(w, make_float2(u.x, u.y), ax[k]);  // 0 * NaN = NaN, like the reference's
+      ay[k] = __ffma2_rn(w, make_float2(u.z, u.w), ay[k]);  // (intersection * efv_directions) product
+      if (COUNT) ac[k] = __fadd2_rn(ac[k], w);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    sx[k] = ax[k].x + ax[k].y;
+    sy[k] = ay[k].x + ay[k].y;
+    cnt[k] = ac[k].x + ac[k].y;
+  }
+}
+
+template <int PPT, bool COUNT>
+__device__ __forceinline__ void pairwise_pass(const Tile<double>& t, int nslots, const double (&xi)[PPT],
+                                              const double (&yi)[PPT], double thr2, double (&sx)[PPT],
+                                              double (&sy)[PPT], double (&cnt)[PPT]) {
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) sx[k] = sy[k] = cnt[k] = 0.0;
+  for (int j = 0; j < nslots; ++j) {
+    const double x = t.X[j], y = t.Y[j], ux = t.UX[j], uy = t.UY[j];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const double dx = x - xi[k], dy = y - yi[k];
+      const double w = (dx * dx + dy * dy < thr2) ? 1.0 : 0.0;
+      sx[k] += w * ux;
+      sy[k] += w * uy;
+      cnt[k] += w;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-wide reductions.  Warp level: REDUX (ints) / shuffles (floats); across warps: shared memory.
+template <int WARPS>
+struct RedScratch {
+  int i[WARPS][4];
+  double f[WARPS][4];
+};
+
+// ------------------------------------------------------------------------------------------
+// Observation encoding of ONE pedestrian row + (thread 0) the agent / exit rows.
+template <typename real>
+__device__ __forceinline__ void store_ped_obs(float* __restrict__ row, int i, int N, real px, real py, int st,
+                                              float apx, float apy, const KArgs<real>& a) {
+  float x = (float)px, y = (float)py;
+  if (a.positions == POS_REL) {  // wrappers.py:20-27, hypotenuse sqrt(2) in float32
+    const real inv = (real)(1.0 / 1.41421353816986083984375);
+    x = (float)((px - (real)apx) * inv);
+    y = (float)((py - (real)apy) * inv);
+  }
+  const int s = 4 - st;  // wrappers.py:47-51: ESCAPED->0, EXITING->1, FOLLOWER->2, VISCEK->3
+  if (a.obs_type == OBS_BOX) {
+    if (a.statuses == STAT_OHE) {
+      float2* r = reinterpret_cast<float2*>(row + (size_t)(i + 2) * 6);
+      r[0] = make_float2(x, y);
+      r[1] = make_float2(s == 0 ? 1.f : 0.f, s == 1 ? 1.f : 0.f);
+      r[2] = make_float2(s == 2 ? 1.f : 0.f, s == 3 ? 1.f : 0.f);
+    } else if (a.statuses == STAT_CAT) {
+      float* r = row + (size_t)(i + 2) * 3;
+      r[0] = x;
+      r[1] = y;
+      r[2] = 0.25f * (float)s;
+    } else {
+      *reinterpret_cast<float2*>(row + (size_t)(i + 2) * 2) = make_float2(x, y);
+    }
+  } else {  // Dict: [agent(2) | exit(2) | peds(2N) | statuses]
+    // (scalar stores: the row stride 4+2N(+4N|+N) floats is not always a multiple of 8 bytes)
+    row[4 + 2 * (size_t)i] = x;
+    row[5 + 2 * (size_t)i] = y;
+    float* sr = row + 4 + 2 * (size_t)N;
+    if (a.statuses == STAT_OHE) {
+      sr[4 * (size_t)i + 0] = s == 0 ? 1.f : 0.f;
+      sr[4 * (size_t)i + 1] = s == 1 ? 1.f : 0.f;
+      sr[4 * (size_t)i + 2] = s == 2 ? 1.f : 0.f;
+      sr[4 * (size_t)i + 3] = s == 3 ? 1.f : 0.f;
+    } else if (a.statuses == STAT_CAT) {
+      sr[i] = 0.25f * (float)s;
+    }
+  }
+}
+
+template <typename real>
+__device__ __forceinline__ void store_head_obs(float* __restrict__ row, float apx, float apy, const KArgs<real>& a) {
+  float ex = 0.f, ey = -1.f;
+  if (a.positions == POS_REL) {
+    const float hyp = 1.41421353816986083984375f;
+    ex = __fdiv_rn(0.f - apx, hyp);
+    ey = __fdiv_rn(-1.f - apy, hyp);
+  }
+  if (a.obs_type == OBS_BOX) {
+    if (a.statuses == STAT_OHE) {  // wrappers.py:82-88: agent stat [0,0,0,0], exit stat [1,0,0,0]
+      float2* r = reinterpret_cast<float2*>(row);
+      r[0] = make_float2(apx, apy);
+      r[1] = make_float2(0.f, 0.f);
+      r[2] = make_float2(0.f, 0.f);
+      r[3] = make_float2(ex, ey);
+      r[4] = make_float2(1.f, 0.f);
+      r[5] = make_float2(0.f, 0.f);
+    } else if (a.statuses == STAT_CAT) {  // wrappers.py:89-91: agent 0, exit 1
+      row[0] = apx; row[1] = apy; row[2] = 0.f;
+      row[3] = ex;  row[4] = ey;  row[5] = 1.f;
+    } else {
+      row[0] = apx; row[1] = apy; row[2] = ex; row[3] = ey;
+    }
+  } else {
+    row[0] = apx; row[1] = apy; row[2] = ex; row[3] = ey;
+  }
+}
+
+// per-pedestrian term of grad_potential_pedestrians [gravity_encoding.py:8-25]
+template <typename real>
+__device__ __forceinline__ void grav_term(real px, real py, float apx, float apy, const KArgs<real>& a, real& gx, real& gy) {
+  const real rx = (real)apx - px, ry = (real)apy - py;
+  const real norm = sqrt_(rx * rx + ry * ry) + a.eps;
+  const real p = a.alpha_plus2_int ? ipow(norm, a.alpha_plus2_int) : (real)pow((double)norm, (double)a.alpha + 2.0);
+  const real c = div_(-a.alpha, p);
+  gx = c * rx;
+  gy = c * ry;
+}
+
+template <typename real>
+__device__ __forceinline__ void store_grav_obs(float* __restrict__ row, float apx, float apy, real gpx, real gpy,
+                                               int n_followers, const KArgs<real>& a) {
+  // grad_potential_exit [gravity_encoding.py:28-38], float32 like the reference (agent, exit are float32)
+  const float rx = apx - 0.f, ry = apy + 1.f;
+  const float norm = __fsqrt_rn(rx * rx + ry * ry) + (float)a.eps;
+  const float alpha = (float)a.alpha;
+  const float p = a.alpha_plus2_int ? ipow(norm, a.alpha_plus2_int) : powf(norm, alpha + 2.f);
+  const float c = __fdiv_rn(-alpha, p);
+  row[0] = apx;
+  row[1] = apy;
+  row[2] = c * rx * (float)n_followers;
+  row[3] = c * ry * (float)n_followers;
+  row[4] = (float)gpx;
+  row[5] = (float)gpy;
+}
+
+// fresh random layout of one pedestrian [pedestrians.py:17-20]
+template <typename real>
+__device__ __forceinline__ void random_layout(uint64_t seed, uint32_t env, uint32_t episode, uint32_t ped, real& px,
+                                              real& py, real& dx, real& dy) {
+  const Philox4 r = evac_random(seed, STREAM_RESET, env, episode, 0u, ped);
+  px = (real)(2.f * u01(r.x) - 1.f);
+  py = (real)(2.f * u01(r.y) - 1.f);
+  real vx = (real)(2.f * u01(r.z) - 1.f), vy = (real)(2.f * u01(r.w) - 1.f);
+  if (vx == (real)0 && vy == (real)0) vx = (real)1;
+  const real n = sqrt_(vx * vx + vy * vy);
+  dx = div_(vx, n);
+  dy = div_(vy, n);
+}
+
+// ------------------------------------------------------------------------------------------
+// THE fused step kernel.  grid = one CTA per environment (grid-stride), THREADS threads,
+// PPT pedestrians per thread (slot i = k*THREADS + tid).
+template <typename real, int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constant__ KArgs<real> a) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr int SLOTS = THREADS * PPT;
+  constexpr bool F64 = std::is_same<real, double>::value;
+  using real2 = typename vec2<real>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ RedScratch<WARPS> red_a, red_b;
+  Tile<real> tile(smem_raw, SLOTS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N;
+
+  for (int e = blockIdx.x; e < a.E; e += gridDim.x) {
+    // ---------------- load state (coalesced real2 per thread)
+    real px[PPT], py[PPT], dx[PPT], dy[PPT];
+    int st[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int i = k * THREADS + tid;
+      if (i < N) {
+        const real2 p = a.pos[(size_t)e * N + i];
+        const real2 d = a.dir[(size_t)e * N + i];
+        px[k] = p.x; py[k] = p.y; dx[k] = d.x; dy[k] = d.y;
+        st[k] = a.status[(size_t)e * N + i];
+      } else {
+        px[k] = py[k] = dx[k] = dy[k] = (real)0;
+        st[k] = ST_NONE;
+      }
+    }
+    float2 ap = a.agent_pos[e], ad = a.agent_dir[e];
+    int now = a.now[e];
+    int episode = a.episode[e];
+    long long overall = a.overall[e];
+    double acc_r = 0, acc_i = 0, acc_s = 0;
+    if (tid == 0) { acc_r = a.acc[3 * (size_t)e]; acc_i = a.acc[3 * (size_t)e + 1]; acc_s = a.acc[3 * (size_t)e + 2]; }
+    const uint32_t env_g = (uint32_t)(a.env_offset + e);
+    float reward_sum = 0.f;
+    int any_term = 0, any_trunc = 0;
+
+    for (int s = 0; s < a.num_steps; ++s) {
+      // ---------------- action source
+      float ax, ay;
+      if (a.agent_kind == AGENT_TABLE) {
+        const float2 av = a.actions[(size_t)s * a.E + e];
+        ax = av.x; ay = av.y;
+      } else if (a.agent_kind == AGENT_RANDOM) {  // RandomAgent: action_space.sample() ~ U[-1,1)^2
+        const Philox4 r = evac_random(a.seed, STREAM_AGENT, env_g, (uint32_t)episode, (uint32_t)now, 0u);
+        ax = 2.f * u01(r.x) - 1.f; ay = 2.f * u01(r.y) - 1.f;
+      } else {  // RotatingAgent [rotating_agent.py:12-16]
+        const float ph = 0.05f * (float)(now + 1);
+        ax = sinf(ph); ay = cosf(ph);
+      }
+      // ---------------- Time.step [area.py:53-59]
+      const int now_prev = now;
+      now += 1; overall += 1;
+      const bool truncated = now >= a.max_timesteps;
+      // ---------------- Area.agent_step [area.py:182-210], float32 like the reference
+      float r_agent = 0.f;
+      bool term_agent = false;
+      {
+        const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay))), a.eps_f);
+        ax = __fdiv_rn(ax, nrm); ay = __fdiv_rn(ay, nrm);
+        ad.x = __fmul_rn(a.step_size_f, ax); ad.y = __fmul_rn(a.step_size_f, ay);
+        const float ptx = __fadd_rn(ap.x, ad.x), pty = __fadd_rn(ap.y, ad.y);
+        const bool collide = (ptx < -a.width_f) | (ptx > a.width_f) | (pty < -a.height_f) | (pty > a.height_f);
+        if (!collide) { ap.x = ptx; ap.y = pty; }
+        else { r_agent = -5.f; term_agent = a.term_wall != 0; }
+      }
+      // ---------------- escaped / exiting preparation + source records [area.py:79-101]
+      bool any_fv = false;
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int i = k * THREADS + tid;
+        if (st[k] == ST_ESCAPED) { dx[k] = dy[k] = (real)0; px[k] = (real)0; py[k] = (real)-1; }
+        if (st[k] == ST_EXITING) {
+          const real vx = (real)0 - px[k], vy = (real)-1 - py[k];
+          const real len = sqrt_(vx * vx + vy * vy);
+          const real sz = min_(len, a.step_size);
+          dx[k] = div_(vx, len) * sz; dy[k] = div_(vy, len) * sz;
+        }
+        const bool efv = st[k] == ST_VISCEK || st[k] == ST_FOLLOWER || st[k] == ST_EXITING;
+        any_fv |= (st[k] == ST_VISCEK || st[k] == ST_FOLLOWER);
+        real ux = (real)0, uy = (real)0, qx = (real)PARK, qy = (real)PARK;
+        if (efv) {
+          const real n = sqrt_(dx[k] * dx[k] + dy[k] * dy[k]);
+          ux = div_(dx[k], n); uy = div_(dy[k], n);  // 0/0 -> NaN exactly like area.py:101
+          qx = px[k]; qy = py[k];
+        }
+        tile.put(i, qx, qy, ux, uy);
+      }
+      __syncthreads();
+      // ---------------- pairwise alignment [area.py:105-119]
+      real sx[PPT], sy[PPT], cnt[PPT];
+      if (__any_sync(0xffffffffu, any_fv)) {
+        pairwise_pass<PPT, F64>(tile, N, px, py, a.thr2_ped, sx, sy, cnt);
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) sx[k] = sy[k] = cnt[k] = (real)0;
+      }
+      // ---------------- new directions, enslaving, integration, reflection, statuses
+      int k_exit = 0, k_fol = 0, n_esc = 0, n_exi = 0, n_fol = 0;
+      real sum_dexit = (real)0;
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int i = k * THREADS + tid;
+        if (i >= N) continue;
+        const int so = st[k];
+        const bool fv = so == ST_VISCEK || so == ST_FOLLOWER;
+        if (fv) {
+          real nz;
+          if (a.noise) {
+            nz = (real)a.noise[((size_t)s * a.E + e) * N + i];
+          } else {
+            const Philox4 r = evac_random(a.seed, STREAM_NOISE, env_g, (uint32_t)episode, (uint32_t)now_prev, (uint32_t)i);
+            nz = (real)((u01(r.x) - 0.5f) * (float)a.noise_coef);
+          }
+          if constexpr (F64) {  // literal transcription of area.py:108-133
+            const double n = fmax(1.0, cnt[k]);
+            const double th = atan2(sy[k] / n, sx[k] / n) + nz;
+            dx[k] = cos(th) * a.step_size; dy[k] = sin(th) * a.step_size;
+          } else {
+            // cos/sin(atan2(my,mx) + nz) == unit(m) rotated by nz; atan2(0,0) = 0 -> unit = (1,0)
+            const float m2 = sx[k] * sx[k] + sy[k] * sy[k];
+            float cx = 1.f, cy = 0.f;
+            if (m2 != 0.f) { const float inv = __fdiv_rn(1.f, __fsqrt_rn(m2)); cx = sx[k] * inv; cy = sy[k] * inv; }
+            float sn, cn;
+            sincosf(nz, &sn, &cn);
+            dx[k] = a.step_size * (cx * cn - cy * sn);
+            dy[k] = a.step_size * (cx * sn + cy * cn);
+          }
+          if (so == ST_FOLLOWER) {  // area.py:138-142; e * agent.direction is float32 in the reference
+            dx[k] = (real)__fmul_rn(a.enslaving_f, ad.x) + a.one_minus_enslaving * dx[k];
+            dy[k] = (real)__fmul_rn(a.enslaving_f, ad.y) + a.one_minus_enslaving * dy[k];
+          }
+        }
+        if (so != ST_ESCAPED) { px[k] += dx[k]; py[k] += dy[k]; }
+        {  // wall reflection for ALL pedestrians [area.py:147-152]
+          const real cx = min_(max_(px[k], -a.width), a.width);
+          const real cy = min_(max_(py[k], -a.height), a.height);
+          const real mx = px[k] - cx, my = py[k] - cy;
+          px[k] -= (real)2 * mx; py[k] -= (real)2 * my;
+          if (mx != (real)0) dx[k] = -dx[k];
+          if (my != (real)0) dy[k] = -dy[k];
+        }
+        real d2e;
+        const int sn_ = status_of<real>(px[k], py[k], (real)ap.x, (real)ap.y, a, d2e);
+        sum_dexit += sqrt_(d2e);
+        k_exit += (fv && sn_ == ST_EXITING);
+        k_fol += (so == ST_VISCEK && sn_ == ST_FOLLOWER);
+        n_esc += (sn_ == ST_ESCAPED); n_exi += (sn_ == ST_EXITING); n_fol += (sn_ == ST_FOLLOWER);
+        st[k] = sn_;
+      }
+      // ---------------- CTA reduction of counts + intrinsic distance sum
+      {
+        int p0 = k_exit | (k_fol << 16), p1 = n_esc | (n_exi << 16), p2 = n_fol;
+        p0 = __reduce_add_sync(0xffffffffu, p0);
+        p1 = __reduce_add_sync(0xffffffffu, p1);
+        p2 = __reduce_add_sync(0xffffffffu, p2);
+        const double sd = warp_sum((double)sum_dexit);
+        if (lane == 0) { red_a.i[warp][0] = p0; red_a.i[warp][1] = p1; red_a.i[warp][2] = p2; red_a.f[warp][0] = sd; }
+      }
+      __syncthreads();
+      int q0 = 0, q1 = 0, q2 = 0;
+      double sd = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) { q0 += red_a.i[w][0]; q1 += red_a.i[w][1]; q2 += red_a.i[w][2]; sd += red_a.f[w][0]; }
+      const int K_exit = q0 & 0xffff, K_fol = q0 >> 16, N_esc = q1 & 0xffff, N_exi = q1 >> 16, N_fol = q2;
+      // ---------------- rewards + termination [reward.py:19-46, area.py:174-180, env.py:158-171]
+      const real tf = (real)1 - (real)now / (real)(200 * N);
+      real r_ped = a.init_reward;
+      if (a.exit_reward) r_ped += ((real)15 + (real)10 * tf) * (real)K_exit;
+      if (a.follow_reward) r_ped += ((real)10 + (real)5 * tf) * (real)K_fol;
+      const real intrinsic = (real)0 - (real)sd / (real)N;
+      const real reward = (real)r_agent + r_ped + a.intrinsic_coef * intrinsic;
+      const bool terminated = term_agent || (N_esc == N);
+      reward_sum += (float)reward;
+      any_term |= terminated; any_trunc |= truncated;
+      if (tid == 0) { acc_r += (double)reward; acc_i += (double)intrinsic; acc_s += (double)((real)r_agent + r_ped); }
+      // ---------------- same-step auto-reset
+      if (a.auto_reset && (terminated || truncated)) {
+        if (tid == 0) {  // the logging dict of env.py:115-125
+          float* es = a.ep_stats + (size_t)e * NUM_EPISODE_STATS;
+          const float v[NUM_EPISODE_STATS] = {(float)acc_i, (float)acc_s, (float)acc_r, (float)now, (float)N_esc, (float)N_exi,
+                                              (float)N_fol, (float)(N - N_esc - N_exi - N_fol), (float)overall};
+#pragma unroll
+          for (int q = 0; q < NUM_EPISODE_STATS; ++q) { es[q] = v[q]; atomicAdd(a.totals + 1 + q, (double)v[q]); }
+          atomicAdd(a.totals, 1.0);
+          a.ep_finished[e] = 1;
+          acc_r = acc_i = acc_s = 0;
+        }
+        now = 0; episode += 1;
+        ap = make_float2(0.f, 0.f); ad = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const int i = k * THREADS + tid;
+          if (i < N) {
+            random_layout<real>(a.seed, env_g, (uint32_t)episode, (uint32_t)i, px[k], py[k], dx[k], dy[k]);
+            real d2e;
+            st[k] = status_of<real>(px[k], py[k], (real)0, (real)0, a, d2e);
+          }
+        }
+      }
+      // ---------------- observation
+      if (a.obs && (a.obs_every_step || s == a.num_steps - 1)) {
+        float* row = a.obs + ((size_t)(a.obs_every_step ? s : 0) * a.E + e) * a.obs_dim;
+        if (a.positions == POS_GRAV) {
+          real gx = (real)0, gy = (real)0;
+          int nf = 0;
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) {
+            if (st[k] == ST_VISCEK) { real tx, ty; grav_term<real>(px[k], py[k], ap.x, ap.y, a, tx, ty); gx += tx; gy += ty; }
+            nf += (st[k] == ST_FOLLOWER);
+          }
+          nf = __reduce_add_sync(0xffffffffu, nf);
+          const double wx = warp_sum((double)gx), wy = warp_sum((double)gy);
+          if (lane == 0) { red_b.i[warp][0] = nf; red_b.f[warp][0] = wx; red_b.f[warp][1] = wy; }
+          __syncthreads();
+          if (tid == 0) {
+            int tf_ = 0; double tx = 0, ty = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { tf_ += red_b.i[w][0]; tx += red_b.f[w][0]; ty += red_b.f[w][1]; }
+            store_grav_obs<real>(row, ap.x, ap.y, (real)tx, (real)ty, tf_, a);
+          }
+        } else {
+          if (tid == 0) store_head_obs<real>(row, ap.x, ap.y, a);
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) {
+            const int i = k * THREADS + tid;
+            if (i < N) store_ped_obs<real>(row, i, N, px[k], py[k], st[k], ap.x, ap.y, a);
+          }
+        }
+      }
+    }  // steps
+
+    // ---------------- write back
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int i = k * THREADS + tid;
+      if (i < N) {
+        real2 p, d;
+        p.x = px[k]; p.y = py[k]; d.x = dx[k]; d.y = dy[k];
+        a.pos[(size_t)e * N + i] = p;
+        a.dir[(size_t)e * N + i] = d;
+        a.status[(size_t)e * N + i] = (uint8_t)st[k];
+      }
+    }
+    if (tid == 0) {
+      a.agent_pos[e] = ap; a.agent_dir[e] = ad;
+      a.now[e] = now; a.episode[e] = episode; a.overall[e] = overall;
+      a.acc[3 * (size_t)e] = acc_r; a.acc[3 * (size_t)e + 1] = acc_i; a.acc[3 * (size_t)e + 2] = acc_s;
+      if (a.reward) a.reward[e] = reward_sum;
+      if (a.terminated) a.terminated[e] = (uint8_t)any_term;
+      if (a.truncated) a.truncated[e] = (uint8_t)any_trunc;
+    }
+    __syncthreads();  // smem tile / scratch reuse by the next environment of this CTA
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Auxiliary kernel (not on the per-step path): reset / recompute statuses / encode observations.
+// One 128-thread CTA per environment, pedestrians strided over the threads.
+enum { AUX_RESET = 1, AUX_STATUS = 2, AUX_OBS = 4 };
+
+template <typename real>
+__global__ void __launch_bounds__(128) evac_aux_kernel(const __grid_constant__ KArgs<real> a, int flags,
+                                                       const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+  using real2 = typename vec2<real>::type;
+  __shared__ RedScratch<4> red;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N;
+  for (int e = blockIdx.x; e < a.E; e += gridDim.x) {
+    const bool sel = (mask == nullptr) || (mask[e] != 0);
+    const uint32_t env_g = (uint32_t)(a.env_offset + e);
+    if ((flags & AUX_RESET) && sel) {
+      __syncthreads();
+      const int episode = a.episode[e] + 1;
+      __syncthreads();
+      for (int i = tid; i < N; i += 128) {
+        real px, py, dx, dy, d2e;
+        random_layout<real>(a.seed, env_g, (uint32_t)episode, (uint32_t)i, px, py, dx, dy);
+        real2 p, d;
+        p.x = px; p.y = py; d.x = dx; d.y = dy;
+        a.pos[(size_t)e * N + i] = p;
+        a.dir[(size_t)e * N + i] = d;
+        a.status[(size_t)e * N + i] = (uint8_t)status_of<real>(px, py, (real)0, (real)0, a, d2e);
+      }
+      if (tid == 0) {
+        a.agent_pos[e] = make_float2(0.f, 0.f); a.agent_dir[e] = make_float2(0.f, 0.f);
+        a.now[e] = 0; a.episode[e] = episode;
+        a.acc[3 * (size_t)e] = a.acc[3 * (size_t)e + 1] = a.acc[3 * (size_t)e + 2] = 0.0;
+      }
+    }
+    if ((flags & AUX_STATUS) && sel) {
+      const float2 ap = a.agent_pos[e];
+      for (int i = tid; i < N; i += 128) {
+        const real2 p = a.pos[(size_t)e * N + i];
+        real d2e;
+        a.status[(size_t)e * N + i] = (uint8_t)status_of<real>(p.x, p.y, (real)ap.x, (real)ap.y, a, d2e);
+      }
+    }
+    if ((flags & AUX_OBS) && obs != nullptr) {
+      __syncthreads();  // this CTA's own global writes above are visible to it after the barrier
+      float2 ap = a.agent_pos[e];
+      if ((flags & AUX_RESET) && sel) ap = make_float2(0.f, 0.f);
+      float* row = obs + (size_t)e * a.obs_dim;
+      if (a.positions == POS_GRAV) {
+        real gx = (real)0, gy = (real)0;
+        int nf = 0;
+        for (int i = tid; i < N; i += 128) {
+          const real2 p = a.pos[(size_t)e * N + i];
+          const int s = a.status[(size_t)e * N + i];
+          if (s == ST_VISCEK) { real tx, ty; grav_term<real>(p.x, p.y, ap.x, ap.y, a, tx, ty); gx += tx; gy += ty; }
+          nf += (s == ST_FOLLOWER);
+        }
+        nf = __reduce_add_sync(0xffffffffu, nf);
+        const double wx = warp_sum((double)gx), wy = warp_sum((double)gy);
+        if (lane == 0) { red.i[warp][0] = nf; red.f[warp][0] = wx; red.f[warp][1] = wy; }
+        __syncthreads();
+        if (tid == 0) {
+          int t = 0; double tx = 0, ty = 0;
+          for (int w = 0; w < 4; ++w) { t += red.i[w][0]; tx += red.f[w][0]; ty += red.f[w][1]; }
+          store_grav_obs<real>(row, ap.x, ap.y, (real)tx, (real)ty, t, a);
+        }
+      } else {
+        if (tid == 0) store_head_obs<real>(row, ap.x, ap.y, a);
+        for (int i = tid; i < N; i += 128) {
+          const real2 p = a.pos[(size_t)e * N + i];
+          store_ped_obs<real>(row, i, N, p.x, p.y, (int)a.status[(size_t)e * N + i], ap.x, ap.y, a);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace evac

@@ -1,0 +1,52 @@
+// Philox4x32-10 counter-based generator (Salmon et al., "Parallel random numbers: as easy as
+// 1, 2, 3", SC'11).  Replaces the reference's global MT19937 stream (area.py:124,
+// pedestrians.py:17-18): every (seed, stream, env, episode, step, pedestrian) tuple owns its
+// own random words, so results do not depend on how environments are sharded over CTAs/GPUs.
+// tests/evac_testlib.py holds the NumPy restatement the parity tests compare against.
+#pragma once
+#include <stdint.h>
+
+namespace evac {
+
+enum : uint32_t { STREAM_NOISE = 0, STREAM_RESET = 1, STREAM_AGENT = 2 };
+
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+  c[0] = hi1 ^ c[1] ^ k0;
+  c[1] = lo1;
+  c[2] = hi0 ^ c[3] ^ k1;
+  c[3] = lo0;
+}
+
+// counter = (c0, c1, c2, c3), key = (k0, k1)
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+  uint32_t c[4] = {c0, c1, c2, c3};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return Philox4{c[0], c[1], c[2], c[3]};
+}
+
+// Stream layout used everywhere in this library:
+//   counter = (pedestrian index, step-in-episode `now`, episode index, global env index)
+//   key     = (seed_lo ^ stream * 0x9E3779B9, seed_hi)
+__host__ __device__ __forceinline__ Philox4 evac_random(uint64_t seed, uint32_t stream, uint32_t env, uint32_t episode,
+                                                        uint32_t now, uint32_t ped) {
+  return philox4x32_10(ped, now, episode, env, (uint32_t)seed ^ (stream * 0x9E3779B9u), (uint32_t)(seed >> 32));
+}
+
+// 24-bit uniform in [0,1): exactly representable in float32, so NumPy reproduces it bit for bit.
+__host__ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
+
+}  // namespace evac

@@ -1,0 +1,418 @@
+"""EvacuationEnv -- host-side mirror of the reference's gymnasium environment
+(src/env/env/env.py:34-171) whose reset/step run as ONE fused CUDA kernel over a batch of
+independent environments (csrc/evac_kernels.cuh behind the C ABI of include/evac_b200.h).
+
+Two faces, one code path:
+
+* ``num_envs == 1`` (default): reference-shaped values -- ``reset() -> (obs, {})`` and
+  ``step(action) -> (obs, reward: float, terminated: bool, truncated: bool, {})`` with NumPy
+  observations (Dict or Box as selected by the wrappers), through the host-buffer entry
+  point ``evac_step_host``.  With ``rng="numpy"`` (the default for this face) the reset layout
+  and the per-step noise are drawn from the GLOBAL ``np.random`` stream in exactly the
+  order the reference consumes it (pedestrians.py:17-18, area.py:124), so
+  ``np.random.seed(s); env.reset(); env.step(a) ...`` retraces the reference's trajectory.
+* ``num_envs > 1``: batched torch CUDA tensors in and out, counter-based (Philox) random
+  streams inside the kernel, optional same-step auto-reset.
+
+There is no CPU fallback: constructing the environment without the CUDA library or without
+a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .config import EnvConfig
+from .spaces import Box, Dict
+from .statuses import Status, SwitchDistances
+
+_TORCH_STATE_DTYPE = {"fp32": torch.float32, "fp64": torch.float64}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _Pedestrians:
+    """`env.unwrapped.pedestrians` (src/env/env/pedestrians.py): live views of the device state."""
+
+    def __init__(self, env: "EvacuationEnv"):
+        self._env = env
+        self.num = env.cfg.number_of_pedestrians
+
+    def _fetch(self, key):
+        v = self._env.get_state()[key]
+        if not self._env.batched:
+            v = v[0].cpu().numpy()
+        return v
+
+    @property
+    def positions(self):
+        return self._fetch("positions")
+
+    @property
+    def directions(self):
+        return self._fetch("directions")
+
+    @property
+    def statuses(self):
+        """uint8 codes with the reference's enum values (Status.X.value)."""
+        return self._fetch("statuses")
+
+    @property
+    def status_stats(self):  # pedestrians.py:37-44
+        s = self._env.get_state()["statuses"]
+        out = {k: (s == v).sum(dim=1) for k, v in
+               (("escaped", 4), ("exiting", 3), ("following", 2), ("viscek", 1))}
+        if not self._env.batched:
+            out = {k: int(v[0]) for k, v in out.items()}
+        return out
+
+
+class _Agent:
+    def __init__(self, env: "EvacuationEnv"):
+        self._env = env
+        self.enslaving_degree = env.cfg.enslaving_degree
+        self.start_position = np.zeros(2, dtype=np.float32)
+        self.start_direction = np.zeros(2, dtype=np.float32)
+
+    @property
+    def position(self):
+        v = self._env.get_state()["agent_position"]
+        return v if self._env.batched else v[0].cpu().numpy()
+
+    @property
+    def direction(self):
+        v = self._env.get_state()["agent_direction"]
+        return v if self._env.batched else v[0].cpu().numpy()
+
+
+class _Exit:
+    def __init__(self):
+        self.position = np.array([0, -1], dtype=np.float32)  # area.py:36-39
+
+
+class _Area:
+    def __init__(self, cfg: EnvConfig):
+        self.width, self.height = cfg.width, cfg.height
+        self.step_size, self.noise_coef, self.eps = cfg.step_size, cfg.noise_coef, cfg.eps
+        self.exit = _Exit()
+
+
+class _Time:
+    def __init__(self, env: "EvacuationEnv"):
+        self._env = env
+        self.max_timesteps = env.cfg.max_timesteps
+
+    @property
+    def now(self):
+        v = self._env.get_state()["now"]
+        return v if self._env.batched else int(v[0])
+
+
+class EvacuationEnv:
+    """Evacuation environment, batched on one B200.  Continuous action and observation space."""
+
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 4}
+
+    def __init__(self, cfg: EnvConfig, num_envs: int = 1, device=None, seed: int = 0,
+                 auto_reset: Optional[bool] = None, precision: str = "fp32", env_index_offset: int = 0,
+                 rng: Optional[str] = None, batched: Optional[bool] = None):
+        if isinstance(cfg, type):  # README.md:72 passes the class itself
+            cfg = cfg()
+        if precision not in nat.PREC:
+            raise ValueError(f"Invalid value of `precision`='{precision}'. Must be 'fp32' or 'fp64'.")
+        self.cfg = cfg
+        self.num_envs = int(num_envs)
+        self.batched = (self.num_envs > 1) if batched is None else bool(batched)
+        self.rng = rng if rng is not None else ("philox" if self.batched else "numpy")
+        if self.rng not in ("numpy", "philox"):
+            raise ValueError(f"Invalid value of `rng`='{self.rng}'. Must be 'numpy' or 'philox'.")
+        self.auto_reset = self.batched if auto_reset is None else bool(auto_reset)
+        self.precision = precision
+        self.seed_value = int(seed)
+        self.env_index_offset = int(env_index_offset)
+        nat.load()  # fail loudly now if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise nat.EvacNativeError("no CUDA device available: evacuation_b200 has no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise ValueError("evacuation_b200 runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+
+        # fused observation pipeline, switched by the wrappers
+        self._positions, self._statuses, self._obs_type, self._alpha = "abs", "no", "Dict", 3.0
+        self._h = None
+        self._host_statuses = None  # numpy-rng face: statuses after the last step (for the |fv| draw)
+
+        n = cfg.number_of_pedestrians
+        self.pedestrians = _Pedestrians(self)
+        self.agent = _Agent(self)
+        self.area = _Area(cfg)
+        self.time = _Time(self)
+        self.intrinsic_reward_coef = cfg.intrinsic_reward_coef
+        self.action_space = Box(low=-1.0, high=1.0, shape=(2,), dtype=np.float32)  # env.py:69
+        self.observation_space = Dict({  # env.py:86-96
+            "agent_position": Box(low=-1, high=1, shape=(2,), dtype=np.float32),
+            "pedestrians_positions": Box(low=-1, high=1, shape=(n, 2), dtype=np.float32),
+            "exit_position": Box(low=-1, high=1, shape=(2,), dtype=np.float32),
+        })
+        self.render_mode = cfg.render_mode
+        self.experiment_name = cfg.experiment_name
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def unwrapped(self):
+        return self
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _configure_obs(self, **kw):
+        """Called by the wrappers: switch on an encoding inside the fused kernel."""
+        state = self.get_state() if self._h is not None else None
+        for k, v in kw.items():
+            setattr(self, "_" + k, v)
+        if self._h is not None:
+            self.close()
+            self._handle()
+            self.set_state(**state)
+
+    def _handle(self):
+        if self._h is not None:
+            return self._h
+        lib = nat.load()
+        c = nat.EvacConfig()
+        nat.check(lib.evac_default_config(C.byref(c)))
+        cfg = self.cfg
+        c.number_of_pedestrians = cfg.number_of_pedestrians
+        c.width, c.height, c.step_size = cfg.width, cfg.height, cfg.step_size
+        c.noise_coef, c.eps, c.enslaving_degree = cfg.noise_coef, cfg.eps, cfg.enslaving_degree
+        c.is_new_exiting_reward = int(cfg.is_new_exiting_reward)
+        c.is_new_followers_reward = int(cfg.is_new_followers_reward)
+        c.intrinsic_reward_coef = cfg.intrinsic_reward_coef
+        c.is_termination_agent_wall_collision = int(cfg.is_termination_agent_wall_collision)
+        c.init_reward_each_step = cfg.init_reward_each_step
+        c.max_timesteps = cfg.max_timesteps
+        if self._positions not in nat.POS or self._statuses not in nat.STAT or self._obs_type not in nat.OBS:
+            raise ValueError(f"invalid observation mode {self._positions}/{self._statuses}/{self._obs_type}")
+        c.positions, c.statuses, c.obs_type = nat.POS[self._positions], nat.STAT[self._statuses], nat.OBS[self._obs_type]
+        c.alpha = float(self._alpha)
+        c.to_leader, c.to_pedestrian = SwitchDistances.to_leader, SwitchDistances.to_pedestrian
+        c.to_exit, c.to_escape = SwitchDistances.to_exit, SwitchDistances.to_escape
+        c.auto_reset = int(self.auto_reset)
+        c.precision = nat.PREC[self.precision]
+        h = C.c_void_p()
+        nat.check(lib.evac_create(C.byref(c), self.num_envs, self.device.index, C.c_uint64(self.seed_value),
+                                  C.c_int64(self.env_index_offset), C.byref(h)))
+        self._h = h
+        self.obs_dim = lib.evac_obs_dim(h)
+        E, dev = self.num_envs, self.device
+        self._obs = torch.empty((E, self.obs_dim), dtype=torch.float32, device=dev)
+        self._reward = torch.empty(E, dtype=torch.float32, device=dev)
+        self._terminated = torch.empty(E, dtype=torch.uint8, device=dev)
+        self._truncated = torch.empty(E, dtype=torch.uint8, device=dev)
+        return h
+
+    def close(self):
+        if self._h is not None:
+            torch.cuda.synchronize(self.device)
+            nat.load().evac_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(nat.load().evac_launch_count(self._handle()))
+
+    # ------------------------------------------------------------------ state access
+    def get_state(self) -> dict:
+        """Copy of the full simulation state as torch tensors on the env's device."""
+        h, lib = self._handle(), nat.load()
+        E, N, dev = self.num_envs, self.cfg.number_of_pedestrians, self.device
+        dt = _TORCH_STATE_DTYPE[self.precision]
+        st = dict(positions=torch.empty((E, N, 2), dtype=dt, device=dev),
+                  directions=torch.empty((E, N, 2), dtype=dt, device=dev),
+                  statuses=torch.empty((E, N), dtype=torch.uint8, device=dev),
+                  agent_position=torch.empty((E, 2), dtype=torch.float32, device=dev),
+                  agent_direction=torch.empty((E, 2), dtype=torch.float32, device=dev),
+                  now=torch.empty(E, dtype=torch.int32, device=dev))
+        nat.check(lib.evac_get_state(h, _ptr(st["positions"]), _ptr(st["directions"]), _ptr(st["statuses"]),
+                                     _ptr(st["agent_position"]), _ptr(st["agent_direction"]), _ptr(st["now"]),
+                                     self._stream()))
+        return st
+
+    def set_state(self, positions=None, directions=None, statuses=None, agent_position=None,
+                  agent_direction=None, now=None):
+        """Overwrite (parts of) the state.  statuses=None with new positions => recomputed from the
+        positions like pedestrians.py:21-26."""
+        h, lib = self._handle(), nat.load()
+        E, N, dev = self.num_envs, self.cfg.number_of_pedestrians, self.device
+        dt = _TORCH_STATE_DTYPE[self.precision]
+
+        def prep(x, shape, dtype):
+            if x is None:
+                return None
+            t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x)
+            return t.to(device=dev, dtype=dtype).reshape(shape).contiguous()
+
+        p, d = prep(positions, (E, N, 2), dt), prep(directions, (E, N, 2), dt)
+        s = prep(statuses, (E, N), torch.uint8)
+        ap, ad = prep(agent_position, (E, 2), torch.float32), prep(agent_direction, (E, 2), torch.float32)
+        nw = prep(now, (E,), torch.int32)
+        nat.check(lib.evac_set_state(h, _ptr(p), _ptr(d), _ptr(s), _ptr(ap), _ptr(ad), _ptr(nw), self._stream()))
+        self._host_statuses = None
+
+    # ------------------------------------------------------------------ observation structure
+    def _structure(self, flat):
+        """flat: torch [E,D] (batched face) or numpy [D] (single-env face) -> Dict / Box observation."""
+        N = self.cfg.number_of_pedestrians
+        lead = flat.shape[:-1]
+        if self._positions == "grav":  # gravity_encoding.py:52-57
+            return {"agent_position": flat[..., 0:2], "grad_potential_exit": flat[..., 2:4],
+                    "grad_potential_pedestrians": flat[..., 4:6]}
+        sc = {"no": 0, "ohe": 4, "cat": 1}[self._statuses]
+        if self._obs_type == "Box":
+            return flat.reshape(*lead, N + 2, 2 + sc)
+        obs = {"agent_position": flat[..., 0:2], "exit_position": flat[..., 2:4],
+               "pedestrians_positions": flat[..., 4:4 + 2 * N].reshape(*lead, N, 2)}
+        if sc == 4:
+            obs["pedestrians_statuses"] = flat[..., 4 + 2 * N:].reshape(*lead, N, 4)
+        elif sc == 1:
+            obs["pedestrians_statuses"] = flat[..., 4 + 2 * N:]
+        return obs
+
+    def _emit_obs(self):
+        if self.batched:
+            return self._structure(self._obs)
+        return self._structure(self._obs[0].cpu().numpy())
+
+    # ------------------------------------------------------------------ gymnasium API
+    def reset(self, seed=None, options=None):
+        """env.py:106-139.  `seed` re-keys the Philox streams (rng="philox"); like in the reference
+        it does NOT touch the global NumPy stream that rng="numpy" draws from."""
+        lib = nat.load()
+        if seed is not None and self.rng == "philox" and int(seed) != self.seed_value:
+            self.close()
+            self.seed_value = int(seed)
+        h = self._handle()
+        E, N = self.num_envs, self.cfg.number_of_pedestrians
+        if self.rng == "philox":
+            nat.check(lib.evac_reset(h, None, _ptr(self._obs), self._stream()))
+        else:
+            nat.check(lib.evac_reset(h, None, None, self._stream()))  # zero time / accumulators
+            pos = np.empty((E, N, 2))
+            dirs = np.empty((E, N, 2))
+            for e in range(E):  # pedestrians.py:17-20, env after env like a SyncVectorEnv would
+                pos[e] = np.random.uniform(-1.0, 1.0, size=(N, 2))
+                d = np.random.uniform(-1.0, 1.0, size=(N, 2))
+                dirs[e] = (d.T / np.linalg.norm(d, axis=1)).T
+            self.set_state(positions=pos, directions=dirs, agent_position=np.zeros((E, 2), np.float32),
+                           agent_direction=np.zeros((E, 2), np.float32), now=np.zeros(E, np.int32))
+            nat.check(lib.evac_observe(h, _ptr(self._obs), self._stream()))
+        self._host_statuses = None
+        return self._emit_obs(), {}
+
+    def _numpy_noise(self):
+        """area.py:124: one U(-c/2, c/2) draw per VISCEK/FOLLOWER pedestrian, ascending index, from
+        the global NumPy stream; scattered into the dense [E,N] table the kernel consumes."""
+        E, N, c = self.num_envs, self.cfg.number_of_pedestrians, self.cfg.noise_coef
+        if self._host_statuses is None:
+            self._host_statuses = self.get_state()["statuses"].cpu().numpy()
+        noise = np.zeros((E, N), dtype=np.float32)
+        for e in range(E):
+            fv = (self._host_statuses[e] == 1) | (self._host_statuses[e] == 2)
+            noise[e, fv] = np.random.uniform(low=-c / 2, high=c / 2, size=int(fv.sum()))
+        return noise
+
+    def step(self, action, noise=None):
+        """env.py:141-171 for every environment of the batch in one kernel launch.
+
+        `noise` (optional): dense [E,N] angular-noise table (injection protocol, include/evac_b200.h)."""
+        h, lib = self._handle(), nat.load()
+        E, N = self.num_envs, self.cfg.number_of_pedestrians
+        if self.batched:
+            act = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action, dtype=np.float32))
+            act = act.to(device=self.device, dtype=torch.float32).reshape(E, 2).contiguous()
+            nz = None
+            if noise is None and self.rng == "numpy":
+                noise = self._numpy_noise()
+            if noise is not None:
+                nz = noise if torch.is_tensor(noise) else torch.as_tensor(np.asarray(noise, dtype=np.float32))
+                nz = nz.to(device=self.device, dtype=torch.float32).reshape(E, N).contiguous()
+            nat.check(lib.evac_step(h, _ptr(act), _ptr(nz), _ptr(self._obs), _ptr(self._reward),
+                                    _ptr(self._terminated), _ptr(self._truncated), self._stream()))
+            if self.rng == "numpy":
+                self._host_statuses = None
+            return (self._structure(self._obs), self._reward, self._terminated.bool(), self._truncated.bool(), {})
+        # ---- single-env face: host buffers through evac_step_host
+        act = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(E, 2))
+        if noise is None and self.rng == "numpy":
+            noise = self._numpy_noise()
+        nz = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float32).reshape(E, N))
+        obs = np.empty((E, self.obs_dim), dtype=np.float32)
+        rew = np.empty(E, dtype=np.float32)
+        term = np.empty(E, dtype=np.uint8)
+        trunc = np.empty(E, dtype=np.uint8)
+        torch.cuda.current_stream(self.device).synchronize()
+        nat.check(lib.evac_step_host(h, act.ctypes.data_as(C.c_void_p),
+                                     None if nz is None else nz.ctypes.data_as(C.c_void_p),
+                                     obs.ctypes.data_as(C.c_void_p), rew.ctypes.data_as(C.c_void_p),
+                                     term.ctypes.data_as(C.c_void_p), trunc.ctypes.data_as(C.c_void_p)))
+        if self.rng == "numpy":
+            self._host_statuses = self.get_state()["statuses"].cpu().numpy()
+        if E == 1:
+            return self._structure(obs[0]), float(rew[0]), bool(term[0]), bool(trunc[0]), {}
+        return self._structure(obs), rew, term.astype(bool), trunc.astype(bool), {}
+
+    def rollout(self, num_steps: int, agent: str = "random", actions=None, noise=None, obs_every_step: bool = False):
+        """`num_steps` consecutive steps in ONE kernel launch, state resident on chip.
+
+        agent: "random" (RandomAgent, random_agent.py:8-9), "rotating" (rotating_agent.py:12-16)
+        or "table" with actions [num_steps,E,2].  Returns (obs, reward_sum[E], terminated_any[E],
+        truncated_any[E]); obs is [E,...] after the last step or [num_steps,E,...]."""
+        h, lib = self._handle(), nat.load()
+        E, N, dev = self.num_envs, self.cfg.number_of_pedestrians, self.device
+        kind = nat.AGENT[agent]
+        act = nz = None
+        if kind == 0:
+            act = torch.as_tensor(actions).to(device=dev, dtype=torch.float32).reshape(num_steps, E, 2).contiguous()
+        if noise is not None:
+            nz = torch.as_tensor(noise).to(device=dev, dtype=torch.float32).reshape(num_steps, E, N).contiguous()
+        obs = self._obs
+        if obs_every_step:
+            obs = torch.empty((num_steps, E, self.obs_dim), dtype=torch.float32, device=dev)
+        nat.check(lib.evac_rollout(h, int(num_steps), kind, _ptr(act), _ptr(nz), _ptr(obs), int(obs_every_step),
+                                   _ptr(self._reward), _ptr(self._terminated), _ptr(self._truncated), self._stream()))
+        self._host_statuses = None
+        return self._structure(obs), self._reward, self._terminated.bool(), self._truncated.bool()
+
+    def episode_statistics(self):
+        """(stats [E,9] float32, finished [E] bool, totals [10] float64) -- per-env record of the last
+        finished episode in the key order of env.py:115-125 (`_native.EPISODE_STAT_KEYS`)."""
+        h, lib = self._handle(), nat.load()
+        E, dev = self.num_envs, self.device
+        stats = torch.empty((E, nat.NUM_EPISODE_STATS), dtype=torch.float32, device=dev)
+        fin = torch.empty(E, dtype=torch.uint8, device=dev)
+        tot = torch.empty(1 + nat.NUM_EPISODE_STATS, dtype=torch.float64, device=dev)
+        nat.check(lib.evac_episode_stats(h, _ptr(stats), _ptr(fin), _ptr(tot), self._stream()))
+        return stats, fin.bool(), tot
+
+    def render(self):
+        raise NotImplementedError("rendering is out of scope of the B200 hot path (DESIGN.md)")
+
+    def save_animation(self):
+        raise NotImplementedError("rendering is out of scope of the B200 hot path (DESIGN.md)")
+
+
+__all__ = ["EvacuationEnv", "Status"]

@@ -1,0 +1,34 @@
+"""Minimal Box / Dict space stand-ins (gymnasium is not a dependency of this package; the
+reference uses gymnasium.spaces at env.py:69,86-96, wrappers.py:34-40,62-73)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Box:
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape) if shape is not None else tuple(np.shape(low))
+        self.low = np.full(self.shape, low, dtype=self.dtype)
+        self.high = np.full(self.shape, high, dtype=self.dtype)
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x) -> bool:
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __repr__(self):
+        return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+
+class Dict(dict):
+    def __init__(self, spaces=None, **kwargs):
+        super().__init__()
+        if spaces is not None:
+            self.update(spaces)
+        self.update(kwargs)
+
+    def sample(self):
+        return {k: v.sample() for k, v in self.items()}

@@ -1,0 +1,196 @@
+/*
+ * evac_b200.h -- C ABI of the B200-native batched evacuation environment step.
+ *
+ * This is the drop-in boundary for the ONE hot path of cinemere/evacuation: the per-step
+ * pedestrian dynamics + observation encoding behind `setup_env(...).reset()/step()`.
+ * The reference has no FFI (it is pure Python); each entry point below names the Python
+ * interface of the reference it replaces (paths relative to the reference root):
+ *
+ *   evac_create / evac_destroy   EvacuationEnv.__init__            src/env/env/env.py:41-84
+ *                                EnvConfig / EnvWrappersConfig     src/env/env/config.py:3-100,
+ *                                                                  src/env/wrappers/config.py:8-93
+ *   evac_reset                   EvacuationEnv.reset               src/env/env/env.py:106-139
+ *                                Pedestrians.reset                 src/env/env/pedestrians.py:16-27
+ *   evac_step / evac_step_host   EvacuationEnv.step                src/env/env/env.py:141-171
+ *                                Area.agent_step                   src/env/env/area.py:182-210
+ *                                Area.pedestrians_step             src/env/env/area.py:76-180
+ *                                update_statuses                   src/env/env/statuses.py:29-48
+ *                                Reward.*                          src/env/env/reward.py:19-46
+ *                                RelativePosition / PedestriansStatuses / MatrixObs
+ *                                                                  src/env/wrappers/wrappers.py:8-96
+ *                                GravityEncoding                   src/env/wrappers/gravity_encoding.py:41-81
+ *   evac_rollout                 the caller's loop around step():  src/agents/rpo_agent.py:180-203 with
+ *                                RandomAgent / RotatingAgent       src/agents/random_agent.py:8-9,
+ *                                                                  src/agents/rotating_agent.py:12-16
+ *   evac_observe                 EvacuationEnv._get_observation + wrappers' observation()
+ *                                                                  src/env/env/env.py:98-104
+ *   evac_get_state/evac_set_state  env.unwrapped.{pedestrians,agent,time} attribute access
+ *                                                                  (wrappers.py:35,48; gravity_encoding.py:50,64-65)
+ *   evac_episode_stats           the per-episode logging dict      src/env/env/env.py:114-127
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all array arguments are raw pointers.
+ *   - unless a function name ends in `_host`, array pointers are DEVICE pointers on the
+ *     handle's device and the call is asynchronous on `stream` (a cudaStream_t passed as void*;
+ *     NULL = the legacy default stream).
+ *   - every function returns 0 on success or a negative EVAC_ERR_* code; evac_last_error()
+ *     returns a thread-local message for the last failure.
+ *   - one handle per (process, GPU); a handle is not thread-safe.
+ *   - there is NO CPU fallback: evac_create fails if no CUDA device is usable.
+ *
+ * Pedestrian status values (src/env/env/statuses.py:16-27): VISCEK=1, FOLLOWER=2, EXITING=3, ESCAPED=4.
+ */
+#ifndef EVAC_B200_H_
+#define EVAC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVAC_ABI_VERSION 1
+
+enum {
+  EVAC_OK = 0,
+  EVAC_ERR_INVALID = -1,     /* bad argument / unsupported configuration          */
+  EVAC_ERR_CUDA = -2,        /* a CUDA runtime call failed                        */
+  EVAC_ERR_UNSUPPORTED = -3, /* valid in the reference but not implemented (e.g. grav + Box, wrappers/config.py:80-81) */
+  EVAC_ERR_NO_DEVICE = -4
+};
+
+enum { EVAC_STATUS_VISCEK = 1, EVAC_STATUS_FOLLOWER = 2, EVAC_STATUS_EXITING = 3, EVAC_STATUS_ESCAPED = 4 };
+enum { EVAC_POS_ABS = 0, EVAC_POS_REL = 1, EVAC_POS_GRAV = 2 };     /* EnvWrappersConfig.positions */
+enum { EVAC_STAT_NO = 0, EVAC_STAT_OHE = 1, EVAC_STAT_CAT = 2 };    /* EnvWrappersConfig.statuses  */
+enum { EVAC_OBS_DICT = 0, EVAC_OBS_BOX = 1 };                       /* EnvWrappersConfig.type      */
+enum { EVAC_PREC_F32 = 0, EVAC_PREC_F64 = 1 };                      /* pedestrian-state arithmetic */
+enum { EVAC_AGENT_TABLE = 0, EVAC_AGENT_RANDOM = 1, EVAC_AGENT_ROTATING = 2 }; /* evac_rollout action source */
+
+/* Number of floats in one episode-statistics record, in the key order of env.py:115-125:
+ * episode_intrinsic_reward, episode_status_reward, episode_reward, episode_length,
+ * escaped_pedestrians, exiting_pedestrians, following_pedestrians, viscek_pedestrians,
+ * overall_timesteps. */
+#define EVAC_NUM_EPISODE_STATS 9
+
+/* Plain-old-data mirror of EnvConfig (config.py:3-100) + EnvWrappersConfig (wrappers/config.py:8-44)
+ * + SwitchDistances (distances.py:17-21).  Field names follow the reference. */
+typedef struct EvacConfig {
+  int32_t abi_version;            /* must be EVAC_ABI_VERSION */
+  int32_t number_of_pedestrians;  /* N, 1 .. 4096 */
+  double width, height;           /* arena half-extents */
+  double step_size;
+  double noise_coef;
+  double eps;
+  double enslaving_degree;
+  int32_t is_new_exiting_reward;
+  int32_t is_new_followers_reward;
+  double intrinsic_reward_coef;
+  int32_t is_termination_agent_wall_collision;
+  double init_reward_each_step;
+  int32_t max_timesteps;
+  /* observation wrappers */
+  int32_t positions; /* EVAC_POS_*  */
+  int32_t statuses;  /* EVAC_STAT_* */
+  int32_t obs_type;  /* EVAC_OBS_*  */
+  double alpha;      /* GravityEncoding alpha */
+  /* SwitchDistances (constants.py:35-38): 0.2, 0.1 ("vision radius"), 0.4, 0.01 */
+  double to_leader, to_pedestrian, to_exit, to_escape;
+  /* batching extras (no counterpart in the reference) */
+  int32_t auto_reset; /* 1: an env that terminates/truncates is reset inside the same step
+                         (gymnasium vector-env "same-step" semantics, rpo_agent.py:193-203) */
+  int32_t precision;  /* EVAC_PREC_F32 (product) or EVAC_PREC_F64 (parity mode) */
+} EvacConfig;
+
+typedef struct EvacHandle EvacHandle;
+
+/* Fill `cfg` with the reference defaults (EnvConfig(), EnvWrappersConfig(), SwitchDistances). */
+int evac_default_config(EvacConfig* cfg);
+
+/* Create `num_envs` independent environments on CUDA device `device`.
+ * `seed` keys the counter-based (Philox4x32-10) streams for reset layouts, noise and the
+ * scripted agents; `env_index_offset` is added to the env index in the stream counter so a
+ * batch sharded over several processes/GPUs draws the same numbers as one big batch. */
+int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_t seed,
+                int64_t env_index_offset, EvacHandle** out);
+int evac_destroy(EvacHandle* h);
+
+/* Floats per environment in one observation row (layout documented in DESIGN.md):
+ *   Dict : [agent(2) | exit(2) | pedestrians(2N) | statuses(4N ohe, N cat, 0 no)]   (sorted-key order)
+ *   Box  : [N+2, 2|3|6] row-major, rows = agent, exit, pedestrians                  (MatrixObs)
+ *   grav : [agent(2) | grad_potential_exit(2) | grad_potential_pedestrians(2)] */
+int32_t evac_obs_dim(const EvacHandle* h);
+int32_t evac_num_envs(const EvacHandle* h);
+/* bytes per element of the pedestrian state arrays exchanged by get/set_state (4 or 8) */
+int32_t evac_state_elem_size(const EvacHandle* h);
+
+/* Reset environments (all, or those with reset_mask[e] != 0) to a fresh random layout
+ * (pedestrians.py:17-20 semantics: pos ~ U[-1,1)^2, dir = normalised U[-1,1)^2, agent at the
+ * origin) drawn from the handle's Philox streams, then write observations to `obs`
+ * ([E, obs_dim] float32, may be NULL). */
+int evac_reset(EvacHandle* h, const uint8_t* reset_mask, float* obs, void* stream);
+
+/* Overwrite / read the full simulation state.  Any pointer may be NULL (= leave / skip).
+ * positions, directions: [E,N,2] float32 (EVAC_PREC_F32) or float64 (EVAC_PREC_F64);
+ * statuses: [E,N] uint8 (set_state: NULL => recomputed from positions like pedestrians.py:21-26);
+ * agent_position, agent_direction: [E,2] float32; now: [E] int32. */
+int evac_set_state(EvacHandle* h, const void* positions, const void* directions, const uint8_t* statuses,
+                   const float* agent_position, const float* agent_direction, const int32_t* now, void* stream);
+int evac_get_state(EvacHandle* h, void* positions, void* directions, uint8_t* statuses,
+                   float* agent_position, float* agent_direction, int32_t* now, void* stream);
+
+/* Encode the observation of the CURRENT state into obs [E, obs_dim] float32. */
+int evac_observe(EvacHandle* h, float* obs, void* stream);
+
+/* One environment step for all E environments (env.py:141-171), ONE fused kernel launch.
+ *   actions    [E,2] float32
+ *   noise      [E,N] float32 or NULL.  NULL: the kernel draws U(-noise_coef/2, noise_coef/2)
+ *              from its Philox stream.  Non-NULL: the injected-noise protocol -- entry [e,i]
+ *              is the angular noise of pedestrian i and is used iff i is VISCEK or FOLLOWER
+ *              (the k-th value the reference draws at area.py:124 goes to the k-th such i).
+ *   obs        [E,obs_dim] float32 out (NULL to skip)
+ *   reward     [E] float32 out; terminated, truncated: [E] uint8 out (any may be NULL) */
+int evac_step(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward,
+              uint8_t* terminated, uint8_t* truncated, void* stream);
+
+/* Same call with HOST buffers: copies actions (and noise) host->device, steps, copies
+ * obs / reward / flags device->host through the handle's pinned staging buffers and
+ * synchronises.  This is the call a host-side Gymnasium user makes once per step. */
+int evac_step_host(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward,
+                   uint8_t* terminated, uint8_t* truncated);
+
+/* `num_steps` consecutive steps in ONE kernel launch with the state kept on chip.
+ *   agent_kind EVAC_AGENT_TABLE: actions [num_steps,E,2] float32; EVAC_AGENT_RANDOM: U[-1,1)^2
+ *              from the Philox stream (RandomAgent); EVAC_AGENT_ROTATING: (sin, cos)(0.05 k)
+ *   noise      NULL or [num_steps,E,N] float32 (injected)
+ *   obs        [E,obs_dim] (observation after the last step) or, if obs_every_step != 0,
+ *              [num_steps,E,obs_dim]; NULL to skip
+ *   reward_sum [E] float32: sum of the rewards of the num_steps steps (NULL to skip)
+ *   terminated, truncated: [E] uint8, OR over the steps (NULL to skip) */
+int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const float* actions, const float* noise,
+                 float* obs, int32_t obs_every_step, float* reward_sum, uint8_t* terminated, uint8_t* truncated,
+                 void* stream);
+
+/* Per-env statistics of the most recently FINISHED episode (auto_reset) -- [E, EVAC_NUM_EPISODE_STATS]
+ * float32 plus finished[E] uint8 (1 if that env finished an episode since the last call; cleared by the call).
+ * `totals` (may be NULL): [1 + EVAC_NUM_EPISODE_STATS] float64 = number of finished episodes and the sums of
+ * their statistics since creation -- the vector that is all-gathered across ranks. */
+int evac_episode_stats(EvacHandle* h, float* stats, uint8_t* finished, double* totals, void* stream);
+
+/* Number of kernels this library launched since the handle was created. */
+int64_t evac_launch_count(const EvacHandle* h);
+
+const char* evac_last_error(void);
+int32_t evac_abi_version(void);
+
+/* ---- measurement helpers (used by bench.py; not part of the reference surface) ---- */
+/* FP32 FMA-pipe peak probe: every thread runs `iters` x 8 independent FMA chains; packed != 0 uses
+ * fma.rn.f32x2.  Returns elapsed milliseconds (CUDA events) in *ms and the flop count in *flops. */
+int evac_probe_fma(int32_t device, int32_t packed, int32_t iters, float* ms, double* flops);
+/* Standalone launch of the SAME pairwise neighbour-alignment device function the fused step uses:
+ * E envs x N pedestrians, `reps` passes over a resident tile.  *ms = elapsed, *pairs = ordered pairs evaluated. */
+int evac_probe_pairwise(int32_t device, int32_t num_envs, int32_t n, int32_t reps, float* ms, double* pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVAC_B200_H_ */

@@ -8,7 +8,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle.evac_oracle import OracleConfig, OracleEnv
+from oracle.evac_oracle import OracleConfig, OracleEnv, compute_statuses  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -47,3 +47,58 @@ def make_oracle_at_golden_start(case, z) -> OracleEnv:
     env.set_state(z["init_positions"], z["init_directions"], z["init_statuses"], np.zeros(2, np.float32))
     env.n_episodes = 1
     return env
+
+
+# ---------------------------------------------------------------------------------------------
+# NumPy restatement of the library's counter-based random streams (csrc/philox.cuh) so the
+# in-kernel RNG can be fed to the oracle bit for bit.
+_M0, _M1, _W0, _W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+STREAM_NOISE, STREAM_RESET, STREAM_AGENT = 0, 1, 2
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10; inputs broadcastable uint32 arrays; returns 4 uint32 arrays."""
+    c = [np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF for x in np.broadcast_arrays(c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0 & 0xFFFFFFFF), np.uint64(k1 & 0xFFFFFFFF)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(_M0) * c[0]
+        p1 = np.uint64(_M1) * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(_W0)) & mask
+        k1 = (k1 + np.uint64(_W1)) & mask
+    return [x.astype(np.uint32) for x in c]
+
+
+def evac_random(seed, stream, env, episode, now, ped):
+    k0 = (seed & 0xFFFFFFFF) ^ ((stream * _W0) & 0xFFFFFFFF)
+    k1 = (seed >> 32) & 0xFFFFFFFF
+    return philox4x32_10(ped, now, episode, env, k0, k1)
+
+
+def u01(r):
+    return (np.asarray(r, dtype=np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
+def philox_noise(seed, env, episode, now, n, noise_coef):
+    """Dense [n] float32 noise the kernel draws for (env, episode, step-in-episode `now`)."""
+    r = evac_random(seed, STREAM_NOISE, env, episode, now, np.arange(n))
+    return (u01(r[0]) - np.float32(0.5)) * np.float32(noise_coef)
+
+
+def philox_action(seed, env, episode, now):
+    r = evac_random(seed, STREAM_AGENT, env, episode, now, 0)
+    return np.array([np.float32(2) * u01(r[0]) - np.float32(1), np.float32(2) * u01(r[1]) - np.float32(1)], dtype=np.float32).reshape(2)
+
+
+def philox_layout(seed, env, episode, n, dtype=np.float32):
+    """(positions [n,2], directions [n,2]) of a kernel-side reset (csrc/evac_kernels.cuh::random_layout)."""
+    r = evac_random(seed, STREAM_RESET, env, episode, 0, np.arange(n))
+    two, one = np.float32(2), np.float32(1)
+    px, py, vx, vy = (two * u01(r[i]) - one for i in range(4))
+    pos = np.stack([px, py], axis=1).astype(dtype)
+    v = np.stack([vx, vy], axis=1).astype(dtype)
+    v[(v[:, 0] == 0) & (v[:, 1] == 0), 0] = 1
+    nrm = np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1])
+    return pos, (v / nrm[:, None]).astype(dtype)

@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the evacuation hot path (BASELINE.json metric: pedestrian-steps/s and env-steps/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPUs
+
+A "step" is one pass of the hot path over one batch: ONE `env.step(actions)` == one fused kernel
+launch advancing every environment of the batch by one time step (agent step, Vicsek alignment,
+noise, enslaving, integration, reflection, statuses, rewards, observation encoding, auto-reset).
+
+Workload at N=1: BASELINE.json configs[1] (C2): 4096 envs x 60 pedestrians, rel positions + ohe
+statuses Box observation [62,6], enslaving 1.0, noise 0.2, RandomAgent-like U[-1,1]^2 actions,
+in-kernel Philox noise, same-step auto-reset.  N>1: the same per-rank batch on every rank
+(environments are independent -> weak scaling, no data-path collective; NCCL only all-gathers the
+episode statistics after the timed region).
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract, plus `roofline`, `roofline_fp32`,
+`cpu_baseline`, `e2e`, `clocks`, `gpu_launches`, `l2_resident`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PED = 60
+ENVS_PER_GPU = 4096
+ENV_KW = dict(number_of_pedestrians=N_PED, enslaving_degree=1.0, noise_coef=0.2, is_new_exiting_reward=True,
+              is_new_followers_reward=True)
+WRAP_KW = dict(positions="rel", statuses="ohe", type="Box")
+WORKLOAD = "C2: 4096 envs x 60 pedestrians per GPU, rel positions + ohe statuses (Box [62,6]), enslaving 1.0, noise 0.2"
+
+
+def algorithmic_bytes_per_env_step(n: int, obs_bytes: int) -> int:
+    """read+write of pos (8N) + dir (8N) + status (N) + agent/time (24), action in (8),
+    reward (4) + flags (2), obs out.  N=60 rel+ohe: 3590 B."""
+    return 2 * (17 * n + 24) + 14 + obs_bytes
+
+
+def algorithmic_flops_per_env_step(n: int) -> int:
+    """8 flop per ordered pair over the full N x N + 120 per pedestrian. N=60: 36000."""
+    return 8 * n * n + 120 * n
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", p
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index: int, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # pragma: no cover
+            self.nv, self.err = None, repr(exc)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference's per-env step loop (the reference itself is pure
+# Python and does not travel to the GPU box; oracle/evac_oracle.py is proven bit-identical to it).
+def _cpu_worker(args):
+    n_envs, steps, warmup, seed, barrier = args
+    from oracle.evac_oracle import OracleConfig, OracleEnv
+
+    cfg = OracleConfig(**ENV_KW, **WRAP_KW)
+    envs = []
+    np.random.seed(seed)
+    for _ in range(n_envs):
+        e = OracleEnv(cfg)
+        e.reset()
+        envs.append(e)
+    rs = np.random.RandomState(seed + 1)
+
+    def one_step():
+        for e in envs:
+            _, _, term, trunc, _ = e.step(rs.uniform(-1, 1, 2).astype(np.float32))
+            if term or trunc:
+                e.reset()
+
+    for _ in range(warmup):
+        one_step()
+    if barrier is not None:
+        barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single_core(target_seconds=12.0):
+    """Oracle port on ONE core: one env x 60 pedestrians (C1-like loop with the C2 wrappers), ~target_seconds."""
+    t = _cpu_worker((1, 200, 20, 0, None))
+    steps = max(200, int(200 * target_seconds / max(t, 1e-3)))
+    steps = min(steps, 200000)
+    t = _cpu_worker((1, steps, 20, 0, None))
+    env_sps = steps / t
+    return {"value": env_sps * N_PED, "unit": "pedestrian-steps/s", "env_steps_per_s": env_sps, "cores": 1, "kind": "port",
+            "sample": f"oracle/evac_oracle.py (NumPy fp64 port, bit-identical to the reference on tests/golden), 1 env x {N_PED} pedestrians, "
+                      f"{steps} steps in {t:.1f} s on 1 core, rel+ohe Box observation"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference algorithm (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    envs_per_worker = 32
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(cores)
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_cpu_worker, [(envs_per_worker, args.steps, args.warmup, 100 + w, barrier) for w in range(cores)])
+    t = max(times)
+    env_steps = cores * envs_per_worker * args.steps
+    value = env_steps * N_PED / t
+    sample = (f"oracle port (kind=port; the reference is pure Python and is not installable/shipped: no setup.py), {cores} worker processes x "
+              f"{envs_per_worker} envs x {N_PED} pedestrians, {args.steps} steps each, max worker time {t:.2f} s")
+    line = {
+        "impl": "reference", "metric": "pedestrian-steps/s", "value": value, "unit": "pedestrian-steps/s", "env_steps_per_s": env_steps / t,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{cores * envs_per_worker} envs per step on the host CPUs"},
+        "cpu_baseline": {"value": value, "unit": "pedestrian-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pedestrian-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import evacuation_b200 as eb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    E, K, W = args.envs, args.steps, max(args.warmup, 3)
+
+    from evacuation_b200.distributed import allgather_episode_totals, shard_offset
+
+    env = eb.setup_env(eb.EnvConfig(**ENV_KW), eb.EnvWrappersConfig(**WRAP_KW), num_envs=E, device=dev, seed=args.seed,
+                       auto_reset=True, env_index_offset=shard_offset(rank, E))
+    u = env.unwrapped
+    env.reset()
+    obs_dim = u.obs_dim
+    # RandomAgent-like actions resident in HBM before the timed region (one [E,2] table per step)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = torch.rand((W + K, E, 2), generator=g, device=dev) * 2 - 1
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for s in range(W):
+        env.step(actions[s])
+    # ---- timed region A (headline `value`): L2 flushed before every step, per-step CUDA events
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = u.launch_count
+    sampler.start()
+    for s in range(K):
+        flush.zero_()
+        starts[s].record()
+        env.step(actions[W + s])
+        ends[s].record()
+    barrier()
+    launches = u.launch_count - launches0
+    kernel_ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends))
+    # ---- timed region B: the same K steps back to back (state L2-resident, launches pipelined)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(K):
+        env.step(actions[W + s])
+    e1.record()
+    barrier()
+    resident_ms = e0.elapsed_time(e1)
+    # ---- timed region C: K steps inside ONE launch (state resident on chip, on-device RandomAgent)
+    env.rollout(8, agent="random")
+    barrier()
+    e0.record()
+    env.rollout(K, agent="random")
+    e1.record()
+    barrier()
+    rollout_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    # ---- e2e: reference-shaped host call -- NumPy actions in, NumPy obs / reward / flags out
+    env_h = eb.setup_env(eb.EnvConfig(**ENV_KW), eb.EnvWrappersConfig(**WRAP_KW), num_envs=E, device=dev, seed=args.seed,
+                         auto_reset=True, batched=False, rng="philox", env_index_offset=shard_offset(rank, E))
+    env_h.reset()
+    host_actions = actions[W:W + K].cpu().numpy()
+    for s in range(3):
+        env_h.step(host_actions[s])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        env_h.step(host_actions[s])
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    kernel_ms, resident_ms, rollout_ms, e2e_s = maxr(kernel_ms), maxr(resident_ms), maxr(rollout_ms), maxr(e2e_s)
+    totals = allgather_episode_totals(u)  # the only collective: finished-episode statistics
+
+    if rank == 0:
+        hbm_peak, peak_src, peaks = load_peaks()
+        total_envs = E * world
+        env_steps = total_envs * K
+        value = env_steps * N_PED / (kernel_ms * 1e-3)
+        bytes_launch = algorithmic_bytes_per_env_step(N_PED, obs_dim * 4) * E
+        flops_launch = algorithmic_flops_per_env_step(N_PED) * E
+        launch_s = kernel_ms * 1e-3 / K
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal; measured FMA probe in profiles/
+        line = {
+            "metric": "pedestrian-steps/s", "value": value, "unit": "pedestrian-steps/s", "env_steps_per_s": env_steps / (kernel_ms * 1e-3),
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": kernel_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "pedestrians": N_PED, "obs": "rel+ohe Box [62,6] f32",
+                       "actions": "U[-1,1]^2 table resident in HBM", "noise": "in-kernel Philox4x32-10", "auto_reset": True,
+                       "l2": "flushed (256 MiB memset) before every timed step; per-step CUDA events on the launching stream",
+                       "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": bytes_launch / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": bytes_launch / launch_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "evac_step_kernel<float,64,1>", "algorithmic_bytes_per_launch": bytes_launch},
+            "roofline_fp32": {"bound": "fp32", "achieved": flops_launch / launch_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                              "frac": flops_launch / launch_s / 1e12 / fp32_peak, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+                              "algorithmic_flops_per_launch": flops_launch},
+            "l2_resident": {"value": env_steps * N_PED / (resident_ms * 1e-3), "unit": "pedestrian-steps/s", "ms_per_step": resident_ms / K,
+                            "note": "same K per-step launches back to back, no L2 flush (state stays L2-resident)"},
+            "rollout": {"value": env_steps * N_PED / (rollout_ms * 1e-3), "unit": "pedestrian-steps/s", "ms_per_step": rollout_ms / K,
+                        "note": "K steps in ONE launch (evac_rollout), on-device RandomAgent, obs written after the last step"},
+            "e2e": {"value": env_steps * N_PED / e2e_s, "unit": "pedestrian-steps/s", "h2d_bytes_per_step": E * 8,
+                    "d2h_bytes_per_step": E * (obs_dim * 4 + 4 + 1 + 1), "ms_per_step": 1e3 * e2e_s / K,
+                    "api": "setup_env(..., batched=False).step(numpy actions) -> numpy obs, reward, flags (evac_step_host)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "episodes_finished_all_ranks": float(totals[:, 0].sum()),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_single_core(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+"""CPU-only tests: host logic, the C-ABI library's exported symbols, the NumPy Philox restatement,
+and the world_size-2 gloo path of the episode-statistics all-gather.  No compute calls into CUDA."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import evac_testlib as T
+
+ROOT = T.ROOT
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from evacuation_b200 import _native as nat
+    from evacuation_b200 import build as b
+
+    path = b.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, "include", "evac_b200.h")).read()
+    declared = set(re.findall(r"\b(evac_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    lib = nat.load()  # binds every symbol; AttributeError if one is missing
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.evac_abi_version() == nat.EVAC_ABI_VERSION
+    cfg = nat.EvacConfig()
+    assert lib.evac_default_config(C.byref(cfg)) == 0
+    # reference defaults: config.py:3-100, wrappers/config.py:8-44, constants.py:35-38
+    assert (cfg.number_of_pedestrians, cfg.width, cfg.height, cfg.step_size, cfg.noise_coef, cfg.eps) == (10, 1.0, 1.0, 0.01, 0.2, 1e-8)
+    assert (cfg.enslaving_degree, cfg.is_new_exiting_reward, cfg.is_new_followers_reward, cfg.intrinsic_reward_coef) == (1.0, 0, 1, 0.0)
+    assert (cfg.init_reward_each_step, cfg.max_timesteps, cfg.alpha) == (-1.0, 2000, 3.0)
+    assert (cfg.to_leader, cfg.to_pedestrian, cfg.to_exit, cfg.to_escape) == (0.2, 0.1, 0.4, 0.01)
+    # the C struct layout seen by ctypes must match the compiler's: sizeof is checked through a NULL-handle call path
+    assert lib.evac_obs_dim(None) == -1 and lib.evac_num_envs(None) == -1
+    assert lib.evac_default_config(None) == -1 and b"NULL" in lib.evac_last_error()
+
+
+def test_cuda_library_contains_sm100a_packed_fp32_code():
+    """The shipped .so carries sm_100a SASS with the packed FP32 pipe instructions of the pairwise pass."""
+    from evacuation_b200 import build as b
+
+    sass = subprocess.run(["cuobjdump", "-sass", b.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for op in ("FFMA2", "FADD2", "FMUL2", "FSET"):
+        assert op in sass, op
+
+
+def test_config_defaults_and_wrapper_dispatch_match_reference():
+    import evacuation_b200 as eb
+
+    c = eb.EnvConfig()
+    assert (c.number_of_pedestrians, c.width, c.height, c.step_size, c.noise_coef, c.eps, c.enslaving_degree) == (10, 1.0, 1.0, 0.01, 0.2, 1e-8, 1.0)
+    assert (c.is_new_exiting_reward, c.is_new_followers_reward, c.intrinsic_reward_coef, c.is_termination_agent_wall_collision) == (False, True, 0.0, False)
+    assert (c.init_reward_each_step, c.max_timesteps, c.giff_freq, c.wandb_enabled) == (-1.0, 2000, 500, True)
+    w = eb.EnvWrappersConfig()
+    assert (w.num_obs_stacks, w.positions, w.statuses, w.type, w.alpha) == (1, "abs", "no", "Dict", 3)
+    with pytest.raises(AssertionError):
+        eb.EnvConfig(n_episodes=1)
+    with pytest.raises(AssertionError):
+        eb.EnvWrappersConfig(num_obs_stacks=4)
+    with pytest.raises(NotImplementedError):
+        eb.EnvWrappersConfig(positions="grav", type="Box").wrap_env(None)
+    with pytest.raises(ValueError):
+        eb.EnvWrappersConfig(positions="grav", type="Tuple").wrap_env(None)
+    assert [s.value for s in eb.Status.all()] == [1, 2, 3, 4] and len(eb.Status) == 4
+    assert (eb.SwitchDistances.to_leader, eb.SwitchDistances.to_pedestrian, eb.SwitchDistances.to_exit, eb.SwitchDistances.to_escape) == (0.2, 0.1, 0.4, 0.01)
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, never route through the oracle."""
+    import torch
+
+    import evacuation_b200 as eb
+    from evacuation_b200._native import EvacNativeError
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(EvacNativeError):
+        eb.setup_env(eb.EnvConfig(), eb.EnvWrappersConfig())
+    src = "".join(open(os.path.join(ROOT, "evacuation_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "evacuation_b200")) if f.endswith(".py"))
+    assert "oracle" not in src.replace("never route through the oracle", "")
+
+
+def test_spaces_and_agents():
+    import evacuation_b200 as eb
+    from evacuation_b200.spaces import Box
+
+    box = Box(low=-1.0, high=1.0, shape=(2,), dtype=np.float32)
+    a = eb.RandomAgent(box).act(None)
+    assert a.dtype == np.float32 and a.shape == (2,) and box.contains(a)
+    r = eb.RotatingAgent(box)
+    assert np.allclose(r.act(None), [np.sin(0.05), np.cos(0.05)]) and np.allclose(r.act(None), [np.sin(0.1), np.cos(0.1)])
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+           ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
+    for ctr, key, want in kat:
+        got = T.philox4x32_10(*ctr, *key)
+        assert tuple(int(x) for x in got) == want
+    nz = T.philox_noise(7, 3, 1, 0, 60, 0.2)
+    assert nz.dtype == np.float32 and np.all(np.abs(nz) <= 0.1) and len(np.unique(nz)) > 50
+
+
+def test_shard_partition():
+    from evacuation_b200.distributed import shard_counts, shard_offset
+
+    assert shard_counts(65536, 8) == [(i * 8192, 8192) for i in range(8)]
+    parts = shard_counts(10, 4)
+    assert parts == [(0, 3), (3, 3), (6, 2), (8, 2)] and sum(c for _, c in parts) == 10
+    assert shard_offset(3, 4096) == 12288
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from evacuation_b200.distributed import allgather_totals_tensor, summarize_totals, shard_counts
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+off, cnt = shard_counts(9, 2)[rank]
+totals = torch.zeros(10, dtype=torch.float64)
+totals[0] = cnt                      # "finished episodes" on this rank
+totals[1:] = torch.arange(1, 10, dtype=torch.float64) * cnt * (rank + 1)
+g = allgather_totals_tensor(totals)
+assert g.shape == (2, 10) and g[0, 0] == 5 and g[1, 0] == 4, g
+s = summarize_totals(g)
+assert s["episodes"] == 9 and abs(s["episode_intrinsic_reward"] - (5 * 1 + 4 * 2) / 9) < 1e-12
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gloo_world_size_2_stats_allgather(tmp_path):
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = str(s.getsockname()[1])
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o
+
+
+def test_oracle_invariants_property():
+    """SURVEY.md 8(a) invariants on the oracle: positions stay in the box, status is a pure function of the
+    positions, ESCAPED is absorbing, rewards decompose."""
+    from oracle.evac_oracle import ESCAPED, OracleConfig, OracleEnv, compute_statuses
+
+    rs = np.random.RandomState(3)
+    env = OracleEnv(OracleConfig(number_of_pedestrians=40, is_new_exiting_reward=True, intrinsic_reward_coef=0.7))
+    np.random.seed(3)
+    env.reset()
+    escaped_before = np.zeros(40, bool)
+    for t in range(400):
+        _, r, term, trunc, info = env.step(np.array([0.2, -1.0], dtype=np.float32) + rs.uniform(-0.3, 0.3, 2).astype(np.float32))
+        assert np.all(np.abs(env.positions) <= 1.0)
+        st, _ = compute_statuses(env.positions, env.agent_position, env.exit_position)
+        assert np.array_equal(st, env.statuses)
+        assert np.all(env.statuses[escaped_before] == ESCAPED)
+        escaped_before = env.statuses == ESCAPED
+        assert r == info.reward_agent + info.reward_pedestrians + 0.7 * info.intrinsic_reward
+        if term:
+            break
+    assert escaped_before.sum() > 0

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -100,6 +101,7 @@ static KArgs<real> make_args(const EvacHandle* h) {
   a.term_wall = c.is_termination_agent_wall_collision;
   a.init_reward = (real)c.init_reward_each_step; a.intrinsic_coef = (real)c.intrinsic_reward_coef;
   a.max_timesteps = c.max_timesteps;
+  a.inv_200n = (real)(1.0 / (200.0 * h->N)); a.inv_n = (real)(1.0 / h->N);
   a.positions = c.positions; a.statuses = c.statuses; a.obs_type = c.obs_type;
   a.alpha = (real)c.alpha; a.eps = (real)c.eps;
   const double ap2 = c.alpha + 2.0;
@@ -118,7 +120,7 @@ static KArgs<real> make_args(const EvacHandle* h) {
 // ------------------------------------------------------------------------------------------
 template <typename real, int THREADS, int PPT>
 static int launch_step_t(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
-  const size_t smem = Tile<real>::bytes(THREADS * PPT);
+  const size_t smem = Tile<real>::bytes(THREADS * PPT) + (size_t)THREADS * PPT * sizeof(float);  // tile + noise
   static thread_local bool attr_set[16] = {false};
   auto kern = evac_step_kernel<real, THREADS, PPT>;
   if (smem > 48 * 1024 && !attr_set[h->device & 15]) {
@@ -132,7 +134,9 @@ static int launch_step_t(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
 }
 
 static void pick_shape(int n, int* threads, int* ppt) {
-  if (n <= 64) { *threads = 64; *ppt = 1; }
+  const char* shape = getenv("EVAC_SHAPE_64");  // A/B switch for N <= 64: "64x1" or "32x2" (default)
+  if (n <= 64 && shape && strcmp(shape, "64x1") == 0) { *threads = 64; *ppt = 1; }
+  else if (n <= 64) { *threads = 32; *ppt = 2; }
   else if (n <= 128) { *threads = 128; *ppt = 1; }
   else if (n <= 256) { *threads = 256; *ppt = 1; }
   else if (n <= 512) { *threads = 256; *ppt = 2; }
@@ -144,6 +148,7 @@ static void pick_shape(int n, int* threads, int* ppt) {
 template <typename real>
 static int launch_step(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
   switch (h->threads * 16 + h->ppt) {
+    case 32 * 16 + 2: return launch_step_t<real, 32, 2>(h, a, st);
     case 64 * 16 + 1: return launch_step_t<real, 64, 1>(h, a, st);
     case 128 * 16 + 1: return launch_step_t<real, 128, 1>(h, a, st);
     case 256 * 16 + 1: return launch_step_t<real, 256, 1>(h, a, st);
@@ -337,6 +342,13 @@ int evac_step(EvacHandle* h, const float* actions, const float* noise, float* ob
   return evac_rollout(h, 1, EVAC_AGENT_TABLE, actions, noise, obs, 0, reward, terminated, truncated, stream);
 }
 
+static bool is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return attr.type == cudaMemoryTypeHost;
+}
+
 int evac_step_host(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward, uint8_t* terminated,
                    uint8_t* truncated) {
   if (!h || !actions) return fail(EVAC_ERR_INVALID, "NULL argument");
@@ -351,19 +363,26 @@ int evac_step_host(EvacHandle* h, const float* actions, const float* noise, floa
   }
   if (noise && !h->h_noise) { CK(cudaMallocHost((void**)&h->h_noise, E * N * 4)); CK(cudaMalloc((void**)&h->d_noise, E * N * 4)); }
   cudaStream_t st = h->stream;
-  memcpy(h->h_actions, actions, E * 8);
-  CK(cudaMemcpyAsync(h->d_actions, h->h_actions, E * 8, cudaMemcpyHostToDevice, st));
-  if (noise) { memcpy(h->h_noise, noise, E * N * 4); CK(cudaMemcpyAsync(h->d_noise, h->h_noise, E * N * 4, cudaMemcpyHostToDevice, st)); }
+  // Page-locked caller buffers are used directly (zero staging copies); pageable ones go through the
+  // handle's pinned staging buffers.
+  const bool pa = is_pinned(actions), pn = is_pinned(noise), po = is_pinned(obs), pr = is_pinned(reward),
+             pt = is_pinned(terminated), pu = is_pinned(truncated);
+  if (!pa) memcpy(h->h_actions, actions, E * 8);
+  CK(cudaMemcpyAsync(h->d_actions, pa ? actions : h->h_actions, E * 8, cudaMemcpyHostToDevice, st));
+  if (noise) {
+    if (!pn) memcpy(h->h_noise, noise, E * N * 4);
+    CK(cudaMemcpyAsync(h->d_noise, pn ? noise : h->h_noise, E * N * 4, cudaMemcpyHostToDevice, st));
+  }
   if (int r = evac_step(h, h->d_actions, noise ? h->d_noise : nullptr, obs ? h->d_obs : nullptr, h->d_reward, h->d_term, h->d_trunc, st)) return r;
-  if (obs) CK(cudaMemcpyAsync(h->h_obs, h->d_obs, E * D * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(h->h_reward, h->d_reward, E * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, st));
+  if (obs) CK(cudaMemcpyAsync(po ? obs : h->h_obs, h->d_obs, E * D * 4, cudaMemcpyDeviceToHost, st));
+  if (reward) CK(cudaMemcpyAsync(pr ? reward : h->h_reward, h->d_reward, E * 4, cudaMemcpyDeviceToHost, st));
+  if (terminated) CK(cudaMemcpyAsync(pt ? terminated : h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, st));
+  if (truncated) CK(cudaMemcpyAsync(pu ? truncated : h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (obs) memcpy(obs, h->h_obs, E * D * 4);
-  if (reward) memcpy(reward, h->h_reward, E * 4);
-  if (terminated) memcpy(terminated, h->h_term, E);
-  if (truncated) memcpy(truncated, h->h_trunc, E);
+  if (obs && !po) memcpy(obs, h->h_obs, E * D * 4);
+  if (reward && !pr) memcpy(reward, h->h_reward, E * 4);
+  if (terminated && !pt) memcpy(terminated, h->h_term, E);
+  if (truncated && !pu) memcpy(truncated, h->h_trunc, E);
   return EVAC_OK;
 }
 
@@ -417,24 +436,36 @@ __global__ void __launch_bounds__(256) probe_fma_kernel(float* out, int iters, f
 }
 
 // Standalone launch of the SAME pairwise_pass device function the fused step kernel uses, on the same
-// CTA shape (64 threads, one pedestrian per thread, one environment per CTA).
-__global__ void __launch_bounds__(64) probe_pairwise_kernel(const float2* __restrict__ pos, const float2* __restrict__ unit,
-                                                            float2* __restrict__ out, int N, int reps, float thr2) {
+// CTA shapes (one environment per CTA; THREADS x PPT = 32x2 or 64x1).
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS) probe_pairwise_kernel(const float2* __restrict__ pos, const float2* __restrict__ unit,
+                                                                 float2* __restrict__ out, int N, int reps, float thr2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Tile<float> tile(smem_raw, 64);
+  Tile<float> tile(smem_raw, THREADS * PPT);
   const int tid = threadIdx.x, e = blockIdx.x;
-  float2 p = make_float2(PARK, PARK), u = make_float2(0.f, 0.f);
-  if (tid < N) { p = pos[(size_t)e * N + tid]; u = unit[(size_t)e * N + tid]; }
-  tile.put(tid, p.x, p.y, u.x, u.y);
-  __syncthreads();
-  float xi[1] = {p.x}, yi[1] = {p.y}, sx[1], sy[1], cnt[1];
-  float accx = 0.f, accy = 0.f;
-  for (int r = 0; r < reps; ++r) {
-    pairwise_pass<1, false>(tile, N, xi, yi, thr2, sx, sy, cnt);
-    accx += sx[0]; accy += sy[0];
-    xi[0] += 1e-9f * sx[0];  // data dependence between passes so they cannot be hoisted
+  float xi[PPT], yi[PPT], sx[PPT], sy[PPT], cnt[PPT], accx[PPT], accy[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int i = k * THREADS + tid;
+    float2 p = make_float2(PARK, PARK), u = make_float2(0.f, 0.f);
+    if (i < N) { p = pos[(size_t)e * N + i]; u = unit[(size_t)e * N + i]; }
+    tile.put(i, p.x, p.y, u.x, u.y);
+    xi[k] = p.x; yi[k] = p.y; accx[k] = accy[k] = 0.f;
   }
-  if (tid < N) out[(size_t)e * N + tid] = make_float2(accx, accy);
+  __syncthreads();
+  for (int r = 0; r < reps; ++r) {
+    pairwise_pass<PPT, false>(tile, N, xi, yi, thr2, sx, sy, cnt);
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      accx[k] += sx[k]; accy[k] += sy[k];
+      xi[k] += 1e-9f * sx[k];  // data dependence between passes so they cannot be hoisted
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int i = k * THREADS + tid;
+    if (i < N) out[(size_t)e * N + i] = make_float2(accx[k], accy[k]);
+  }
 }
 
 extern "C" {
@@ -482,9 +513,12 @@ int evac_probe_pairwise(int32_t device, int32_t num_envs, int32_t n, int32_t rep
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   const float thr2 = round_up_f32(sq_boundary(0.1));
+  const char* shape = getenv("EVAC_SHAPE_64");
+  const bool shape_32x2 = !(shape && strcmp(shape, "64x1") == 0);
   for (int rep = 0; rep < 2; ++rep) {
     CK(cudaEventRecord(e0));
-    probe_pairwise_kernel<<<num_envs, 64, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
+    if (shape_32x2) probe_pairwise_kernel<32, 2><<<num_envs, 32, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
+    else probe_pairwise_kernel<64, 1><<<num_envs, 64, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
   }

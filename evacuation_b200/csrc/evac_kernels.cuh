@@ -58,6 +58,7 @@ struct KArgs {
   int exit_reward, follow_reward, term_wall;
   real init_reward, intrinsic_coef;
   int max_timesteps;
+  real inv_200n, inv_n;  // 1/(200 N), 1/N  (float path only; the double path divides like the reference)
   // ---- observation (EnvWrappersConfig)
   int positions, statuses, obs_type;
   real alpha, eps;
@@ -101,6 +102,30 @@ __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+
+// sqrt for quantities that only feed a 1e-5-tolerance output (intrinsic reward): MUFU.SQRT for float
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
+
+// 1/sqrt(x): float = MUFU.RSQ + one Newton step (rounding-limited, ~1 ulp); rsqrt(0) = inf and the
+// Newton step turns it into NaN, so v * inv_norm(0) = NaN exactly like the reference's 0/0 (area.py:101).
+__device__ __forceinline__ float inv_norm(float n2) {
+  const float y = rsqrtf(n2);
+  return y * fmaf(-0.5f * n2 * y, y, 1.5f);
+}
+__device__ __forceinline__ double inv_norm(double n2) { return 1.0 / sqrt(n2); }
+
+// sin/cos of the angular noise.  |x| <= pi/4 (always true for noise_coef <= pi/2): Cephes single-precision
+// minimax polynomials (<= 1 ulp on that interval); otherwise the library sincosf.
+__device__ __forceinline__ void sincos_noise(float x, float& sn, float& cn) {
+  if (fabsf(x) <= 0.785398163f) {
+    const float z = x * x;
+    sn = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, x, x);
+    cn = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f) * z, z, fmaf(-0.5f, z, 1.0f));
+  } else {
+    sincosf(x, &sn, &cn);
+  }
+}
 
 template <typename real>
 __device__ __forceinline__ real ipow(real x, int n) {  // x^n, n >= 1, by squaring
@@ -152,9 +177,9 @@ struct Tile<float> {
   float4* U2;
   __device__ __forceinline__ Tile(unsigned char* base, int slots) {
     P2 = reinterpret_cast<float4*>(base);
-    U2 = P2 + slots / 2;
+    U2 = P2 + slots / 2 + 1;  // +1: spare look-ahead entry (pairwise_pass)
   }
-  static __host__ __device__ constexpr size_t bytes(int slots) { return (size_t)slots * 16; }
+  static __host__ __device__ constexpr size_t bytes(int slots) { return (size_t)slots * 16 + 32; }
   __device__ __forceinline__ void put(int j, float x, float y, float ux, float uy) {
     float* p = reinterpret_cast<float*>(P2 + (j >> 1)) + (j & 1);
     float* u = reinterpret_cast<float*>(U2 + (j >> 1)) + (j & 1);
@@ -200,10 +225,14 @@ __device__ __forceinline__ void pairwise_pass(const Tile<float>& t, int nslots, 
     ny[k] = make_float2(-yi[k], -yi[k]);
   }
   const int n2 = (nslots + 1) >> 1;
+  // software pipeline: the operands of iteration j+1 are loaded (broadcast LDS.128) while iteration j is
+  // computed, so the ~30-cycle shared-memory latency is off the dependent chain.  The tile carries one
+  // spare entry per array, so the look-ahead load of the last iteration stays inside the allocation.
+  float4 p = t.P2[0], u = t.U2[0];
 #pragma unroll 4
   for (int j = 0; j < n2; ++j) {
-    const float4 p = t.P2[j];  // broadcast LDS.128
-    const float4 u = t.U2[j];
+    const float4 pn = t.P2[j + 1];
+    const float4 un = t.U2[j + 1];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const float2 dx = __fadd2_rn(make_float2(p.x, p.y), nx[k]);
@@ -215,6 +244,8 @@ __device__ __forceinline__ void pairwise_pass(const Tile<float>& t, int nslots, 
       ay[k] = __ffma2_rn(w, make_float2(u.z, u.w), ay[k]);  // (intersection * efv_directions) product
       if (COUNT) ac[k] = __fadd2_rn(ac[k], w);
     }
+    p = pn;
+    u = un;
   }
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
@@ -241,6 +272,12 @@ __device__ __forceinline__ void pairwise_pass(const Tile<double>& t, int nslots,
       cnt[k] += w;
     }
   }
+}
+
+// A one-warp CTA only needs warp-level convergence + memory ordering, not a hardware barrier.
+template <int WARPS>
+__device__ __forceinline__ void cta_sync() {
+  if constexpr (WARPS == 1) __syncwarp(); else __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -297,9 +334,9 @@ template <typename real>
 __device__ __forceinline__ void store_head_obs(float* __restrict__ row, float apx, float apy, const KArgs<real>& a) {
   float ex = 0.f, ey = -1.f;
   if (a.positions == POS_REL) {
-    const float hyp = 1.41421353816986083984375f;
-    ex = __fdiv_rn(0.f - apx, hyp);
-    ey = __fdiv_rn(-1.f - apy, hyp);
+    const float inv_hyp = (float)(1.0 / 1.41421353816986083984375);
+    ex = (0.f - apx) * inv_hyp;
+    ey = (-1.f - apy) * inv_hyp;
   }
   if (a.obs_type == OBS_BOX) {
     if (a.statuses == STAT_OHE) {  // wrappers.py:82-88: agent stat [0,0,0,0], exit stat [1,0,0,0]
@@ -367,14 +404,16 @@ __device__ __forceinline__ void random_layout(uint64_t seed, uint32_t env, uint3
 // THE fused step kernel.  grid = one CTA per environment (grid-stride), THREADS threads,
 // PPT pedestrians per thread (slot i = k*THREADS + tid).
 template <typename real, int THREADS, int PPT>
-__global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constant__ KArgs<real> a) {
+__global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 ? 16 : 1))) evac_step_kernel(const __grid_constant__ KArgs<real> a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int SLOTS = THREADS * PPT;
   constexpr bool F64 = std::is_same<real, double>::value;
   using real2 = typename vec2<real>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ RedScratch<WARPS> red_a, red_b;
+  __shared__ float2 action_s;
   Tile<real> tile(smem_raw, SLOTS);
+  float* noise_s = reinterpret_cast<float*>(smem_raw + Tile<real>::bytes(SLOTS));  // [SLOTS]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
@@ -407,26 +446,74 @@ __global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constan
     int any_term = 0, any_trunc = 0;
 
     for (int s = 0; s < a.num_steps; ++s) {
-      // ---------------- action source
-      float ax, ay;
-      if (a.agent_kind == AGENT_TABLE) {
-        const float2 av = a.actions[(size_t)s * a.E + e];
-        ax = av.x; ay = av.y;
-      } else if (a.agent_kind == AGENT_RANDOM) {  // RandomAgent: action_space.sample() ~ U[-1,1)^2
-        const Philox4 r = evac_random(a.seed, STREAM_AGENT, env_g, (uint32_t)episode, (uint32_t)now, 0u);
-        ax = 2.f * u01(r.x) - 1.f; ay = 2.f * u01(r.y) - 1.f;
-      } else {  // RotatingAgent [rotating_agent.py:12-16]
-        const float ph = 0.05f * (float)(now + 1);
-        ax = sinf(ph); ay = cosf(ph);
-      }
       // ---------------- Time.step [area.py:53-59]
       const int now_prev = now;
       now += 1; overall += 1;
       const bool truncated = now >= a.max_timesteps;
-      // ---------------- Area.agent_step [area.py:182-210], float32 like the reference
+      // ---------------- random streams for this step: one Philox4x32-10 block serves FOUR pedestrians
+      // (noise of pedestrian i = word i&3 of block i>>2), computed once per block and shared through smem;
+      // the RandomAgent action is one more block evaluated by the last thread.
+      if (a.noise == nullptr) {
+        const float c = (float)a.noise_coef;
+        for (int b = tid; b < ((N + 3) >> 2); b += THREADS) {
+          const Philox4 r = evac_random(a.seed, STREAM_NOISE, env_g, (uint32_t)episode, (uint32_t)now_prev, (uint32_t)b);
+          reinterpret_cast<float4*>(noise_s)[b] =
+              make_float4((u01(r.x) - 0.5f) * c, (u01(r.y) - 0.5f) * c, (u01(r.z) - 0.5f) * c, (u01(r.w) - 0.5f) * c);
+        }
+      }
+      if (a.agent_kind == AGENT_RANDOM && tid == THREADS - 1) {  // RandomAgent: action_space.sample() ~ U[-1,1)^2
+        const Philox4 r = evac_random(a.seed, STREAM_AGENT, env_g, (uint32_t)episode, (uint32_t)now_prev, 0u);
+        action_s = make_float2(2.f * u01(r.x) - 1.f, 2.f * u01(r.y) - 1.f);
+      }
+      // ---------------- escaped / exiting preparation + source records [area.py:79-101]
+      bool any_fv = false;
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int i = k * THREADS + tid;
+        if (st[k] == ST_ESCAPED) { dx[k] = dy[k] = (real)0; px[k] = (real)0; py[k] = (real)-1; }
+        if (st[k] == ST_EXITING) {  // dir = (v / |v|) * min(|v|, step_size)
+          const real vx = (real)0 - px[k], vy = (real)-1 - py[k];
+          if constexpr (F64) {
+            const real len = sqrt_(vx * vx + vy * vy);
+            const real sz = min_(len, a.step_size);
+            dx[k] = div_(vx, len) * sz; dy[k] = div_(vy, len) * sz;
+          } else {
+            const real n2 = vx * vx + vy * vy;
+            const real inv = inv_norm(n2);
+            const real sc = min_(n2 * inv, a.step_size) * inv;
+            dx[k] = vx * sc; dy[k] = vy * sc;
+          }
+        }
+        const bool efv = st[k] == ST_VISCEK || st[k] == ST_FOLLOWER || st[k] == ST_EXITING;
+        any_fv |= (st[k] == ST_VISCEK || st[k] == ST_FOLLOWER);
+        real ux = (real)0, uy = (real)0, qx = (real)PARK, qy = (real)PARK;
+        if (efv) {  // u = dir / |dir|; a zero direction gives NaN exactly like area.py:101
+          if constexpr (F64) {
+            const real n = sqrt_(dx[k] * dx[k] + dy[k] * dy[k]);
+            ux = div_(dx[k], n); uy = div_(dy[k], n);
+          } else {
+            const real inv = inv_norm(dx[k] * dx[k] + dy[k] * dy[k]);
+            ux = dx[k] * inv; uy = dy[k] * inv;
+          }
+          qx = px[k]; qy = py[k];
+        }
+        tile.put(i, qx, qy, ux, uy);
+      }
+      cta_sync<WARPS>();
+      // ---------------- action source + Area.agent_step [area.py:182-210], float32 like the reference
       float r_agent = 0.f;
       bool term_agent = false;
       {
+        float ax, ay;
+        if (a.agent_kind == AGENT_TABLE) {
+          const float2 av = a.actions[(size_t)s * a.E + e];
+          ax = av.x; ay = av.y;
+        } else if (a.agent_kind == AGENT_RANDOM) {
+          ax = action_s.x; ay = action_s.y;
+        } else {  // RotatingAgent [rotating_agent.py:12-16]
+          const float ph = 0.05f * (float)now;
+          ax = sinf(ph); ay = cosf(ph);
+        }
         const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay))), a.eps_f);
         ax = __fdiv_rn(ax, nrm); ay = __fdiv_rn(ay, nrm);
         ad.x = __fmul_rn(a.step_size_f, ax); ad.y = __fmul_rn(a.step_size_f, ay);
@@ -435,29 +522,6 @@ __global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constan
         if (!collide) { ap.x = ptx; ap.y = pty; }
         else { r_agent = -5.f; term_agent = a.term_wall != 0; }
       }
-      // ---------------- escaped / exiting preparation + source records [area.py:79-101]
-      bool any_fv = false;
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int i = k * THREADS + tid;
-        if (st[k] == ST_ESCAPED) { dx[k] = dy[k] = (real)0; px[k] = (real)0; py[k] = (real)-1; }
-        if (st[k] == ST_EXITING) {
-          const real vx = (real)0 - px[k], vy = (real)-1 - py[k];
-          const real len = sqrt_(vx * vx + vy * vy);
-          const real sz = min_(len, a.step_size);
-          dx[k] = div_(vx, len) * sz; dy[k] = div_(vy, len) * sz;
-        }
-        const bool efv = st[k] == ST_VISCEK || st[k] == ST_FOLLOWER || st[k] == ST_EXITING;
-        any_fv |= (st[k] == ST_VISCEK || st[k] == ST_FOLLOWER);
-        real ux = (real)0, uy = (real)0, qx = (real)PARK, qy = (real)PARK;
-        if (efv) {
-          const real n = sqrt_(dx[k] * dx[k] + dy[k] * dy[k]);
-          ux = div_(dx[k], n); uy = div_(dy[k], n);  // 0/0 -> NaN exactly like area.py:101
-          qx = px[k]; qy = py[k];
-        }
-        tile.put(i, qx, qy, ux, uy);
-      }
-      __syncthreads();
       // ---------------- pairwise alignment [area.py:105-119]
       real sx[PPT], sy[PPT], cnt[PPT];
       if (__any_sync(0xffffffffu, any_fv)) {
@@ -476,13 +540,8 @@ __global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constan
         const int so = st[k];
         const bool fv = so == ST_VISCEK || so == ST_FOLLOWER;
         if (fv) {
-          real nz;
-          if (a.noise) {
-            nz = (real)a.noise[((size_t)s * a.E + e) * N + i];
-          } else {
-            const Philox4 r = evac_random(a.seed, STREAM_NOISE, env_g, (uint32_t)episode, (uint32_t)now_prev, (uint32_t)i);
-            nz = (real)((u01(r.x) - 0.5f) * (float)a.noise_coef);
-          }
+          const float nzf = a.noise ? a.noise[((size_t)s * a.E + e) * N + i] : noise_s[i];
+          const real nz = (real)nzf;
           if constexpr (F64) {  // literal transcription of area.py:108-133
             const double n = fmax(1.0, cnt[k]);
             const double th = atan2(sy[k] / n, sx[k] / n) + nz;
@@ -491,9 +550,9 @@ __global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constan
             // cos/sin(atan2(my,mx) + nz) == unit(m) rotated by nz; atan2(0,0) = 0 -> unit = (1,0)
             const float m2 = sx[k] * sx[k] + sy[k] * sy[k];
             float cx = 1.f, cy = 0.f;
-            if (m2 != 0.f) { const float inv = __fdiv_rn(1.f, __fsqrt_rn(m2)); cx = sx[k] * inv; cy = sy[k] * inv; }
+            if (m2 != 0.f) { const float inv = inv_norm(m2); cx = sx[k] * inv; cy = sy[k] * inv; }
             float sn, cn;
-            sincosf(nz, &sn, &cn);
+            sincos_noise(nzf, sn, cn);
             dx[k] = a.step_size * (cx * cn - cy * sn);
             dy[k] = a.step_size * (cx * sn + cy * cn);
           }
@@ -513,33 +572,43 @@ __global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constan
         }
         real d2e;
         const int sn_ = status_of<real>(px[k], py[k], (real)ap.x, (real)ap.y, a, d2e);
-        sum_dexit += sqrt_(d2e);
+        sum_dexit += sqrt_fast(d2e);
         k_exit += (fv && sn_ == ST_EXITING);
         k_fol += (so == ST_VISCEK && sn_ == ST_FOLLOWER);
         n_esc += (sn_ == ST_ESCAPED); n_exi += (sn_ == ST_EXITING); n_fol += (sn_ == ST_FOLLOWER);
         st[k] = sn_;
       }
       // ---------------- CTA reduction of counts + intrinsic distance sum
+      int w0 = 0, w1 = 0, w2 = 0;
+      float wsd = 0.f;
       {
         int p0 = k_exit | (k_fol << 16), p1 = n_esc | (n_exi << 16), p2 = n_fol;
         p0 = __reduce_add_sync(0xffffffffu, p0);
         p1 = __reduce_add_sync(0xffffffffu, p1);
         p2 = __reduce_add_sync(0xffffffffu, p2);
-        const double sd = warp_sum((double)sum_dexit);
-        if (lane == 0) { red_a.i[warp][0] = p0; red_a.i[warp][1] = p1; red_a.i[warp][2] = p2; red_a.f[warp][0] = sd; }
+        const float sdw = warp_sum((float)sum_dexit);
+        if constexpr (WARPS == 1) {
+          w0 = p0; w1 = p1; w2 = p2; wsd = sdw;
+        } else {
+          if (lane == 0) { red_a.i[warp][0] = p0; red_a.i[warp][1] = p1; red_a.i[warp][2] = p2; red_a.f[warp][0] = (double)sdw; }
+        }
       }
-      __syncthreads();
       int q0 = 0, q1 = 0, q2 = 0;
       double sd = 0;
+      if constexpr (WARPS == 1) {
+        q0 = w0; q1 = w1; q2 = w2; sd = (double)wsd;
+      } else {
+        cta_sync<WARPS>();
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) { q0 += red_a.i[w][0]; q1 += red_a.i[w][1]; q2 += red_a.i[w][2]; sd += red_a.f[w][0]; }
+        for (int w = 0; w < WARPS; ++w) { q0 += red_a.i[w][0]; q1 += red_a.i[w][1]; q2 += red_a.i[w][2]; sd += red_a.f[w][0]; }
+      }
       const int K_exit = q0 & 0xffff, K_fol = q0 >> 16, N_esc = q1 & 0xffff, N_exi = q1 >> 16, N_fol = q2;
       // ---------------- rewards + termination [reward.py:19-46, area.py:174-180, env.py:158-171]
-      const real tf = (real)1 - (real)now / (real)(200 * N);
+      const real tf = F64 ? (real)1 - (real)now / (real)(200 * N) : (real)1 - (real)now * a.inv_200n;
       real r_ped = a.init_reward;
       if (a.exit_reward) r_ped += ((real)15 + (real)10 * tf) * (real)K_exit;
       if (a.follow_reward) r_ped += ((real)10 + (real)5 * tf) * (real)K_fol;
-      const real intrinsic = (real)0 - (real)sd / (real)N;
+      const real intrinsic = F64 ? (real)0 - (real)sd / (real)N : (real)0 - (real)sd * a.inv_n;
       const real reward = (real)r_agent + r_ped + a.intrinsic_coef * intrinsic;
       const bool terminated = term_agent || (N_esc == N);
       reward_sum += (float)reward;
@@ -583,7 +652,7 @@ __global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constan
           nf = __reduce_add_sync(0xffffffffu, nf);
           const double wx = warp_sum((double)gx), wy = warp_sum((double)gy);
           if (lane == 0) { red_b.i[warp][0] = nf; red_b.f[warp][0] = wx; red_b.f[warp][1] = wy; }
-          __syncthreads();
+          cta_sync<WARPS>();
           if (tid == 0) {
             int tf_ = 0; double tx = 0, ty = 0;
 #pragma unroll
@@ -621,7 +690,7 @@ __global__ void __launch_bounds__(THREADS) evac_step_kernel(const __grid_constan
       if (a.terminated) a.terminated[e] = (uint8_t)any_term;
       if (a.truncated) a.truncated[e] = (uint8_t)any_trunc;
     }
-    __syncthreads();  // smem tile / scratch reuse by the next environment of this CTA
+    cta_sync<WARPS>();  // smem tile / scratch reuse by the next environment of this CTA
   }
 }
 

@@ -39,7 +39,8 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 }
 
 // Stream layout used everywhere in this library:
-//   counter = (pedestrian index, step-in-episode `now`, episode index, global env index)
+//   counter = (index, step-in-episode `now`, episode index, global env index) with index =
+//             pedestrian (reset layout), pedestrian/4 (noise: one block serves 4 pedestrians), 0 (agent action)
 //   key     = (seed_lo ^ stream * 0x9E3779B9, seed_hi)
 __host__ __device__ __forceinline__ Philox4 evac_random(uint64_t seed, uint32_t stream, uint32_t env, uint32_t episode,
                                                         uint32_t now, uint32_t ped) {

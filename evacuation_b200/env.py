@@ -217,6 +217,11 @@ class EvacuationEnv:
         self._reward = torch.empty(E, dtype=torch.float32, device=dev)
         self._terminated = torch.empty(E, dtype=torch.uint8, device=dev)
         self._truncated = torch.empty(E, dtype=torch.uint8, device=dev)
+        # zero-copy bool views of the flag bytes and the structured view of the observation rows
+        self._terminated_b, self._truncated_b = self._terminated.view(torch.bool), self._truncated.view(torch.bool)
+        self._obs_view = self._structure(self._obs)
+        # page-locked host buffers of the single-env / host face (evac_step_host copies straight into them)
+        self._host = None
         return h
 
     def close(self):
@@ -294,8 +299,9 @@ class EvacuationEnv:
 
     def _emit_obs(self):
         if self.batched:
-            return self._structure(self._obs)
-        return self._structure(self._obs[0].cpu().numpy())
+            return self._obs_view
+        o = self._obs.cpu().numpy()
+        return self._structure(o[0] if self.num_envs == 1 else o)
 
     # ------------------------------------------------------------------ gymnasium API
     def reset(self, seed=None, options=None):
@@ -342,8 +348,11 @@ class EvacuationEnv:
         h, lib = self._handle(), nat.load()
         E, N = self.num_envs, self.cfg.number_of_pedestrians
         if self.batched:
-            act = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action, dtype=np.float32))
-            act = act.to(device=self.device, dtype=torch.float32).reshape(E, 2).contiguous()
+            act = action
+            if not (torch.is_tensor(act) and act.is_cuda and act.dtype == torch.float32 and act.is_contiguous()
+                    and act.numel() == 2 * E):  # fast path: a ready [E,2] float32 CUDA tensor is used in place
+                act = act if torch.is_tensor(act) else torch.as_tensor(np.asarray(act, dtype=np.float32))
+                act = act.to(device=self.device, dtype=torch.float32).reshape(E, 2).contiguous()
             nz = None
             if noise is None and self.rng == "numpy":
                 noise = self._numpy_noise()
@@ -354,21 +363,25 @@ class EvacuationEnv:
                                     _ptr(self._terminated), _ptr(self._truncated), self._stream()))
             if self.rng == "numpy":
                 self._host_statuses = None
-            return (self._structure(self._obs), self._reward, self._terminated.bool(), self._truncated.bool(), {})
+            return (self._obs_view, self._reward, self._terminated_b, self._truncated_b, {})
         # ---- single-env face: host buffers through evac_step_host
         act = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(E, 2))
         if noise is None and self.rng == "numpy":
             noise = self._numpy_noise()
         nz = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float32).reshape(E, N))
-        obs = np.empty((E, self.obs_dim), dtype=np.float32)
-        rew = np.empty(E, dtype=np.float32)
-        term = np.empty(E, dtype=np.uint8)
-        trunc = np.empty(E, dtype=np.uint8)
+        if self._host is None:
+            pin = dict(pin_memory=True)
+            self._host = dict(obs=torch.empty((E, self.obs_dim), dtype=torch.float32, **pin), rew=torch.empty(E, dtype=torch.float32, **pin),
+                              term=torch.empty(E, dtype=torch.uint8, **pin), trunc=torch.empty(E, dtype=torch.uint8, **pin))
+            self._host_np = {k: v.numpy() for k, v in self._host.items()}
+        hb = self._host
+        # outputs alias the page-locked buffers and are valid until the next step (the reference's
+        # observations alias live state in the same way, env.py:100-102)
+        obs, rew, term, trunc = (self._host_np[k] for k in ("obs", "rew", "term", "trunc"))
         torch.cuda.current_stream(self.device).synchronize()
         nat.check(lib.evac_step_host(h, act.ctypes.data_as(C.c_void_p),
                                      None if nz is None else nz.ctypes.data_as(C.c_void_p),
-                                     obs.ctypes.data_as(C.c_void_p), rew.ctypes.data_as(C.c_void_p),
-                                     term.ctypes.data_as(C.c_void_p), trunc.ctypes.data_as(C.c_void_p)))
+                                     _ptr(hb["obs"]), _ptr(hb["rew"]), _ptr(hb["term"]), _ptr(hb["trunc"])))
         if self.rng == "numpy":
             self._host_statuses = self.get_state()["statuses"].cpu().numpy()
         if E == 1:
@@ -395,7 +408,7 @@ class EvacuationEnv:
         nat.check(lib.evac_rollout(h, int(num_steps), kind, _ptr(act), _ptr(nz), _ptr(obs), int(obs_every_step),
                                    _ptr(self._reward), _ptr(self._terminated), _ptr(self._truncated), self._stream()))
         self._host_statuses = None
-        return self._structure(obs), self._reward, self._terminated.bool(), self._truncated.bool()
+        return self._structure(obs), self._reward, self._terminated_b, self._truncated_b
 
     def episode_statistics(self):
         """(stats [E,9] float32, finished [E] bool, totals [10] float64) -- per-env record of the last

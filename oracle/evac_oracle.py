@@ -128,6 +128,9 @@ class StepInfo:
     # (pair test vs 0.1, status tests vs 0.2 / 0.4 / 0.01, wall tests): a float32
     # implementation may legitimately decide differently when this is ~1e-7.
     margin: float = np.inf
+    # smallest mean resultant length |mean of neighbour unit vectors| over the VISCEK/FOLLOWER pedestrians:
+    # the new heading is atan2 of that mean, so a float32 heading error ~1e-7 / min_resultant is expected
+    min_resultant: float = np.inf
     n_noise_used: int = 0
     fv_mask: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=bool))
 
@@ -251,6 +254,10 @@ class OracleEnv:
             mx = (inter * e_unit[:, 0]).sum(axis=1) / n_inter
             my = (inter * e_unit[:, 1]).sum(axis=1) / n_inter
         theta = np.arctan2(my, mx)
+        if mx.size:
+            with np.errstate(invalid="ignore"):
+                res = np.sqrt(mx * mx + my * my)
+                info.min_resultant = float(np.nanmin(res)) if np.isfinite(res).any() else np.inf
 
         n_fv = int(fv.sum())
         info.n_noise_used = n_fv
@@ -270,7 +277,9 @@ class OracleEnv:
         # wall reflection (area.py:147-152)
         clipped = np.clip(pos, [-cfg.width, -cfg.height], [cfg.width, cfg.height])
         miss = pos - clipped
-        moved = pos[efv]
+        # wall margin: only pedestrians whose direction sign matters afterwards (an EXITING pedestrian's
+        # direction is rebuilt from its position next step, and the reflection of the position is continuous)
+        moved = pos[fv]
         if moved.size:
             with np.errstate(invalid="ignore"):
                 margins.append(float(np.nanmin(np.abs(np.abs(moved) - np.array([cfg.width, cfg.height])))))

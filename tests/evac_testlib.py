@@ -82,9 +82,12 @@ def u01(r):
 
 
 def philox_noise(seed, env, episode, now, n, noise_coef):
-    """Dense [n] float32 noise the kernel draws for (env, episode, step-in-episode `now`)."""
-    r = evac_random(seed, STREAM_NOISE, env, episode, now, np.arange(n))
-    return (u01(r[0]) - np.float32(0.5)) * np.float32(noise_coef)
+    """Dense [n] float32 noise the kernel draws for (env, episode, step-in-episode `now`): one Philox block
+    serves four pedestrians (pedestrian i = word i&3 of block i>>2)."""
+    nb = (n + 3) // 4
+    r = evac_random(seed, STREAM_NOISE, env, episode, now, np.arange(nb))
+    words = np.stack(r, axis=1).reshape(-1)[:n]
+    return (u01(words) - np.float32(0.5)) * np.float32(noise_coef)
 
 
 def philox_action(seed, env, episode, now):

@@ -402,12 +402,15 @@ __device__ __forceinline__ void random_layout(uint64_t seed, uint32_t env, uint3
 
 // ------------------------------------------------------------------------------------------
 // THE fused step kernel.  grid = one CTA per environment (grid-stride), THREADS threads,
-// PPT pedestrians per thread (slot i = k*THREADS + tid).
+// PPT pedestrians per thread (pedestrian i = k*THREADS + tid).  N <= 64 runs as ONE WARP per
+// environment (THREADS = 32, PPT = 2): no block barrier, reductions are pure REDUX / shuffles, and
+// the moving pedestrians are compacted (ballot + popc) so the pairwise pass only visits them.
 template <typename real, int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 ? 16 : 1))) evac_step_kernel(const __grid_constant__ KArgs<real> a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int SLOTS = THREADS * PPT;
   constexpr bool F64 = std::is_same<real, double>::value;
+  constexpr bool COMPACT = (WARPS == 1);
   using real2 = typename vec2<real>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ RedScratch<WARPS> red_a, red_b;
@@ -417,87 +420,103 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int n_blocks = (N + 3) >> 2;                                            // Philox blocks of noise
+  const int n_rng = (a.noise == nullptr ? n_blocks : 0);
+  const int n_rng_all = n_rng + (a.agent_kind == AGENT_RANDOM ? 1 : 0);         // + one block for the RandomAgent
+  const float noise_c = (float)a.noise_coef;
 
   for (int e = blockIdx.x; e < a.E; e += gridDim.x) {
     // ---------------- load state (coalesced real2 per thread)
+    real2* __restrict__ pos_e = a.pos + (size_t)e * N;
+    real2* __restrict__ dir_e = a.dir + (size_t)e * N;
+    uint8_t* __restrict__ st_e = a.status + (size_t)e * N;
     real px[PPT], py[PPT], dx[PPT], dy[PPT];
     int st[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const int i = k * THREADS + tid;
+      px[k] = py[k] = dx[k] = dy[k] = (real)0;
+      st[k] = ST_NONE;
       if (i < N) {
-        const real2 p = a.pos[(size_t)e * N + i];
-        const real2 d = a.dir[(size_t)e * N + i];
+        const real2 p = pos_e[i];
+        const real2 d = dir_e[i];
         px[k] = p.x; py[k] = p.y; dx[k] = d.x; dy[k] = d.y;
-        st[k] = a.status[(size_t)e * N + i];
-      } else {
-        px[k] = py[k] = dx[k] = dy[k] = (real)0;
-        st[k] = ST_NONE;
+        st[k] = st_e[i];
       }
     }
     float2 ap = a.agent_pos[e], ad = a.agent_dir[e];
     int now = a.now[e];
     int episode = a.episode[e];
-    long long overall = a.overall[e];
+    const int now_start = now;
+    int steps_total = 0;
     double acc_r = 0, acc_i = 0, acc_s = 0;
-    if (tid == 0) { acc_r = a.acc[3 * (size_t)e]; acc_i = a.acc[3 * (size_t)e + 1]; acc_s = a.acc[3 * (size_t)e + 2]; }
     const uint32_t env_g = (uint32_t)(a.env_offset + e);
     float reward_sum = 0.f;
     int any_term = 0, any_trunc = 0;
+    bool acc_reset = false;
+    const float* noise_e = a.noise ? a.noise + (size_t)e * N : nullptr;
+    float* obs_e = a.obs ? a.obs + (size_t)e * a.obs_dim : nullptr;
 
     for (int s = 0; s < a.num_steps; ++s) {
       // ---------------- Time.step [area.py:53-59]
       const int now_prev = now;
-      now += 1; overall += 1;
+      now += 1; steps_total += 1;
       const bool truncated = now >= a.max_timesteps;
       // ---------------- random streams for this step: one Philox4x32-10 block serves FOUR pedestrians
       // (noise of pedestrian i = word i&3 of block i>>2), computed once per block and shared through smem;
-      // the RandomAgent action is one more block evaluated by the last thread.
-      if (a.noise == nullptr) {
-        const float c = (float)a.noise_coef;
-        for (int b = tid; b < ((N + 3) >> 2); b += THREADS) {
-          const Philox4 r = evac_random(a.seed, STREAM_NOISE, env_g, (uint32_t)episode, (uint32_t)now_prev, (uint32_t)b);
-          reinterpret_cast<float4*>(noise_s)[b] =
-              make_float4((u01(r.x) - 0.5f) * c, (u01(r.y) - 0.5f) * c, (u01(r.z) - 0.5f) * c, (u01(r.w) - 0.5f) * c);
-        }
-      }
-      if (a.agent_kind == AGENT_RANDOM && tid == THREADS - 1) {  // RandomAgent: action_space.sample() ~ U[-1,1)^2
-        const Philox4 r = evac_random(a.seed, STREAM_AGENT, env_g, (uint32_t)episode, (uint32_t)now_prev, 0u);
-        action_s = make_float2(2.f * u01(r.x) - 1.f, 2.f * u01(r.y) - 1.f);
+      // the RandomAgent action (action_space.sample() ~ U[-1,1)^2) is one more block of the same pass.
+      for (int b = tid; b < n_rng_all; b += THREADS) {
+        const bool is_action = (b >= n_rng);
+        const Philox4 r = evac_random(a.seed, is_action ? STREAM_AGENT : STREAM_NOISE, env_g, (uint32_t)episode,
+                                      (uint32_t)now_prev, is_action ? 0u : (uint32_t)b);
+        if (is_action) action_s = make_float2(2.f * u01(r.x) - 1.f, 2.f * u01(r.y) - 1.f);
+        else reinterpret_cast<float4*>(noise_s)[b] = make_float4((u01(r.x) - 0.5f) * noise_c, (u01(r.y) - 0.5f) * noise_c,
+                                                                 (u01(r.z) - 0.5f) * noise_c, (u01(r.w) - 0.5f) * noise_c);
       }
       // ---------------- escaped / exiting preparation + source records [area.py:79-101]
       bool any_fv = false;
+      bool efv[PPT];
+      real ux[PPT], uy[PPT];
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
-        const int i = k * THREADS + tid;
-        if (st[k] == ST_ESCAPED) { dx[k] = dy[k] = (real)0; px[k] = (real)0; py[k] = (real)-1; }
-        if (st[k] == ST_EXITING) {  // dir = (v / |v|) * min(|v|, step_size)
-          const real vx = (real)0 - px[k], vy = (real)-1 - py[k];
-          if constexpr (F64) {
-            const real len = sqrt_(vx * vx + vy * vy);
-            const real sz = min_(len, a.step_size);
-            dx[k] = div_(vx, len) * sz; dy[k] = div_(vy, len) * sz;
-          } else {
-            const real n2 = vx * vx + vy * vy;
-            const real inv = inv_norm(n2);
-            const real sc = min_(n2 * inv, a.step_size) * inv;
-            dx[k] = vx * sc; dy[k] = vy * sc;
-          }
+        const int so = st[k];
+        if (so == ST_ESCAPED) { dx[k] = dy[k] = (real)0; px[k] = (real)0; py[k] = (real)-1; }
+        real vx = dx[k], vy = dy[k];
+        if (so == ST_EXITING) { vx = (real)0 - px[k]; vy = (real)-1 - py[k]; }
+        efv[k] = (unsigned)(so - ST_VISCEK) <= (unsigned)(ST_EXITING - ST_VISCEK);
+        any_fv |= (unsigned)(so - ST_VISCEK) <= (unsigned)(ST_FOLLOWER - ST_VISCEK);
+        // u = v / |v| (a zero direction gives NaN exactly like area.py:101); exiting: dir = u * min(|v|, step_size)
+        if constexpr (F64) {
+          const real len = sqrt_(vx * vx + vy * vy);
+          ux[k] = div_(vx, len); uy[k] = div_(vy, len);
+          if (so == ST_EXITING) { const real sz = min_(len, a.step_size); dx[k] = ux[k] * sz; dy[k] = uy[k] * sz; }
+        } else {
+          const real n2 = vx * vx + vy * vy;
+          const real inv = inv_norm(n2);
+          ux[k] = vx * inv; uy[k] = vy * inv;
+          if (so == ST_EXITING) { const real sc = min_(n2 * inv, a.step_size) * inv; dx[k] = vx * sc; dy[k] = vy * sc; }
         }
-        const bool efv = st[k] == ST_VISCEK || st[k] == ST_FOLLOWER || st[k] == ST_EXITING;
-        any_fv |= (st[k] == ST_VISCEK || st[k] == ST_FOLLOWER);
-        real ux = (real)0, uy = (real)0, qx = (real)PARK, qy = (real)PARK;
-        if (efv) {  // u = dir / |dir|; a zero direction gives NaN exactly like area.py:101
-          if constexpr (F64) {
-            const real n = sqrt_(dx[k] * dx[k] + dy[k] * dy[k]);
-            ux = div_(dx[k], n); uy = div_(dy[k], n);
-          } else {
-            const real inv = inv_norm(dx[k] * dx[k] + dy[k] * dy[k]);
-            ux = dx[k] * inv; uy = dy[k] * inv;
-          }
-          qx = px[k]; qy = py[k];
+      }
+      int n_src = N;  // number of source slots the pairwise pass visits
+      if constexpr (COMPACT) {
+        // one warp: rank the moving (exiting / following / viscek) pedestrians and store them densely
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const uint32_t m = __ballot_sync(0xffffffffu, efv[k]);
+          if (efv[k]) tile.put(base + __popc(m & lt_mask), px[k], py[k], ux[k], uy[k]);
+          base += __popc(m);
         }
-        tile.put(i, qx, qy, ux, uy);
+        n_src = base;
+        if (lane < 2) tile.put(base + lane, (real)PARK, (real)PARK, (real)0, (real)0);  // pad to an even count
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const int i = k * THREADS + tid;
+          if (efv[k]) tile.put(i, px[k], py[k], ux[k], uy[k]);
+          else tile.put(i, (real)PARK, (real)PARK, (real)0, (real)0);
+        }
       }
       cta_sync<WARPS>();
       // ---------------- action source + Area.agent_step [area.py:182-210], float32 like the reference
@@ -525,7 +544,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       // ---------------- pairwise alignment [area.py:105-119]
       real sx[PPT], sy[PPT], cnt[PPT];
       if (__any_sync(0xffffffffu, any_fv)) {
-        pairwise_pass<PPT, F64>(tile, N, px, py, a.thr2_ped, sx, sy, cnt);
+        pairwise_pass<PPT, F64>(tile, n_src, px, py, a.thr2_ped, sx, sy, cnt);
       } else {
 #pragma unroll
         for (int k = 0; k < PPT; ++k) sx[k] = sy[k] = cnt[k] = (real)0;
@@ -533,18 +552,17 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       // ---------------- new directions, enslaving, integration, reflection, statuses
       int k_exit = 0, k_fol = 0, n_esc = 0, n_exi = 0, n_fol = 0;
       real sum_dexit = (real)0;
+      const real e_adx = (real)__fmul_rn(a.enslaving_f, ad.x), e_ady = (real)__fmul_rn(a.enslaving_f, ad.y);
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         const int i = k * THREADS + tid;
-        if (i >= N) continue;
         const int so = st[k];
-        const bool fv = so == ST_VISCEK || so == ST_FOLLOWER;
+        const bool fv = (unsigned)(so - ST_VISCEK) <= (unsigned)(ST_FOLLOWER - ST_VISCEK);
         if (fv) {
-          const float nzf = a.noise ? a.noise[((size_t)s * a.E + e) * N + i] : noise_s[i];
-          const real nz = (real)nzf;
+          const float nzf = noise_e ? noise_e[((size_t)s * a.E) * N + i] : noise_s[i];
           if constexpr (F64) {  // literal transcription of area.py:108-133
             const double n = fmax(1.0, cnt[k]);
-            const double th = atan2(sy[k] / n, sx[k] / n) + nz;
+            const double th = atan2(sy[k] / n, sx[k] / n) + (double)nzf;
             dx[k] = cos(th) * a.step_size; dy[k] = sin(th) * a.step_size;
           } else {
             // cos/sin(atan2(my,mx) + nz) == unit(m) rotated by nz; atan2(0,0) = 0 -> unit = (1,0)
@@ -557,11 +575,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
             dy[k] = a.step_size * (cx * sn + cy * cn);
           }
           if (so == ST_FOLLOWER) {  // area.py:138-142; e * agent.direction is float32 in the reference
-            dx[k] = (real)__fmul_rn(a.enslaving_f, ad.x) + a.one_minus_enslaving * dx[k];
-            dy[k] = (real)__fmul_rn(a.enslaving_f, ad.y) + a.one_minus_enslaving * dy[k];
+            dx[k] = e_adx + a.one_minus_enslaving * dx[k];
+            dy[k] = e_ady + a.one_minus_enslaving * dy[k];
           }
         }
-        if (so != ST_ESCAPED) { px[k] += dx[k]; py[k] += dy[k]; }
+        if (efv[k]) { px[k] += dx[k]; py[k] += dy[k]; }
         {  // wall reflection for ALL pedestrians [area.py:147-152]
           const real cx = min_(max_(px[k], -a.width), a.width);
           const real cy = min_(max_(py[k], -a.height), a.height);
@@ -571,7 +589,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
           if (my != (real)0) dy[k] = -dy[k];
         }
         real d2e;
-        const int sn_ = status_of<real>(px[k], py[k], (real)ap.x, (real)ap.y, a, d2e);
+        int sn_ = status_of<real>(px[k], py[k], (real)ap.x, (real)ap.y, a, d2e);
+        if (i >= N) { sn_ = ST_NONE; d2e = (real)0; }
         sum_dexit += sqrt_fast(d2e);
         k_exit += (fv && sn_ == ST_EXITING);
         k_fol += (so == ST_VISCEK && sn_ == ST_FOLLOWER);
@@ -579,8 +598,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         st[k] = sn_;
       }
       // ---------------- CTA reduction of counts + intrinsic distance sum
-      int w0 = 0, w1 = 0, w2 = 0;
-      float wsd = 0.f;
+      int q0, q1, q2;
+      double sd;
       {
         int p0 = k_exit | (k_fol << 16), p1 = n_esc | (n_exi << 16), p2 = n_fol;
         p0 = __reduce_add_sync(0xffffffffu, p0);
@@ -588,44 +607,42 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         p2 = __reduce_add_sync(0xffffffffu, p2);
         const float sdw = warp_sum((float)sum_dexit);
         if constexpr (WARPS == 1) {
-          w0 = p0; w1 = p1; w2 = p2; wsd = sdw;
+          q0 = p0; q1 = p1; q2 = p2; sd = (double)sdw;
         } else {
           if (lane == 0) { red_a.i[warp][0] = p0; red_a.i[warp][1] = p1; red_a.i[warp][2] = p2; red_a.f[warp][0] = (double)sdw; }
-        }
-      }
-      int q0 = 0, q1 = 0, q2 = 0;
-      double sd = 0;
-      if constexpr (WARPS == 1) {
-        q0 = w0; q1 = w1; q2 = w2; sd = (double)wsd;
-      } else {
-        cta_sync<WARPS>();
+          cta_sync<WARPS>();
+          q0 = q1 = q2 = 0; sd = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) { q0 += red_a.i[w][0]; q1 += red_a.i[w][1]; q2 += red_a.i[w][2]; sd += red_a.f[w][0]; }
+          for (int w = 0; w < WARPS; ++w) { q0 += red_a.i[w][0]; q1 += red_a.i[w][1]; q2 += red_a.i[w][2]; sd += red_a.f[w][0]; }
+        }
       }
       const int K_exit = q0 & 0xffff, K_fol = q0 >> 16, N_esc = q1 & 0xffff, N_exi = q1 >> 16, N_fol = q2;
       // ---------------- rewards + termination [reward.py:19-46, area.py:174-180, env.py:158-171]
-      const real tf = F64 ? (real)1 - (real)now / (real)(200 * N) : (real)1 - (real)now * a.inv_200n;
+      real tf, intrinsic;
+      if constexpr (F64) { tf = (real)1 - (real)now / (real)(200 * N); intrinsic = (real)0 - (real)sd / (real)N; }
+      else { tf = (real)1 - (real)now * a.inv_200n; intrinsic = (real)0 - (real)sd * a.inv_n; }
       real r_ped = a.init_reward;
       if (a.exit_reward) r_ped += ((real)15 + (real)10 * tf) * (real)K_exit;
       if (a.follow_reward) r_ped += ((real)10 + (real)5 * tf) * (real)K_fol;
-      const real intrinsic = F64 ? (real)0 - (real)sd / (real)N : (real)0 - (real)sd * a.inv_n;
-      const real reward = (real)r_agent + r_ped + a.intrinsic_coef * intrinsic;
+      const real r_status = (real)r_agent + r_ped;
+      const real reward = r_status + a.intrinsic_coef * intrinsic;
       const bool terminated = term_agent || (N_esc == N);
       reward_sum += (float)reward;
       any_term |= terminated; any_trunc |= truncated;
-      if (tid == 0) { acc_r += (double)reward; acc_i += (double)intrinsic; acc_s += (double)((real)r_agent + r_ped); }
+      acc_r += (double)reward; acc_i += (double)intrinsic; acc_s += (double)r_status;
       // ---------------- same-step auto-reset
       if (a.auto_reset && (terminated || truncated)) {
         if (tid == 0) {  // the logging dict of env.py:115-125
+          if (!acc_reset) { acc_r += a.acc[3 * (size_t)e]; acc_i += a.acc[3 * (size_t)e + 1]; acc_s += a.acc[3 * (size_t)e + 2]; }
           float* es = a.ep_stats + (size_t)e * NUM_EPISODE_STATS;
           const float v[NUM_EPISODE_STATS] = {(float)acc_i, (float)acc_s, (float)acc_r, (float)now, (float)N_esc, (float)N_exi,
-                                              (float)N_fol, (float)(N - N_esc - N_exi - N_fol), (float)overall};
+                                              (float)N_fol, (float)(N - N_esc - N_exi - N_fol), (float)(a.overall[e] + steps_total)};
 #pragma unroll
           for (int q = 0; q < NUM_EPISODE_STATS; ++q) { es[q] = v[q]; atomicAdd(a.totals + 1 + q, (double)v[q]); }
           atomicAdd(a.totals, 1.0);
           a.ep_finished[e] = 1;
-          acc_r = acc_i = acc_s = 0;
         }
+        acc_r = acc_i = acc_s = 0; acc_reset = true;
         now = 0; episode += 1;
         ap = make_float2(0.f, 0.f); ad = make_float2(0.f, 0.f);
 #pragma unroll
@@ -639,8 +656,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         }
       }
       // ---------------- observation
-      if (a.obs && (a.obs_every_step || s == a.num_steps - 1)) {
-        float* row = a.obs + ((size_t)(a.obs_every_step ? s : 0) * a.E + e) * a.obs_dim;
+      if (obs_e != nullptr && (a.obs_every_step || s == a.num_steps - 1)) {
+        float* row = obs_e + (a.obs_every_step ? (size_t)s * a.E * a.obs_dim : (size_t)0);
         if (a.positions == POS_GRAV) {
           real gx = (real)0, gy = (real)0;
           int nf = 0;
@@ -650,15 +667,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
             nf += (st[k] == ST_FOLLOWER);
           }
           nf = __reduce_add_sync(0xffffffffu, nf);
-          const double wx = warp_sum((double)gx), wy = warp_sum((double)gy);
-          if (lane == 0) { red_b.i[warp][0] = nf; red_b.f[warp][0] = wx; red_b.f[warp][1] = wy; }
-          cta_sync<WARPS>();
-          if (tid == 0) {
-            int tf_ = 0; double tx = 0, ty = 0;
+          double wx = warp_sum((double)gx), wy = warp_sum((double)gy);
+          if constexpr (WARPS > 1) {
+            if (lane == 0) { red_b.i[warp][0] = nf; red_b.f[warp][0] = wx; red_b.f[warp][1] = wy; }
+            cta_sync<WARPS>();
+            nf = 0; wx = 0; wy = 0;
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) { tf_ += red_b.i[w][0]; tx += red_b.f[w][0]; ty += red_b.f[w][1]; }
-            store_grav_obs<real>(row, ap.x, ap.y, (real)tx, (real)ty, tf_, a);
+            for (int w = 0; w < WARPS; ++w) { nf += red_b.i[w][0]; wx += red_b.f[w][0]; wy += red_b.f[w][1]; }
           }
+          if (tid == 0) store_grav_obs<real>(row, ap.x, ap.y, (real)wx, (real)wy, nf, a);
         } else {
           if (tid == 0) store_head_obs<real>(row, ap.x, ap.y, a);
 #pragma unroll
@@ -677,19 +694,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       if (i < N) {
         real2 p, d;
         p.x = px[k]; p.y = py[k]; d.x = dx[k]; d.y = dy[k];
-        a.pos[(size_t)e * N + i] = p;
-        a.dir[(size_t)e * N + i] = d;
-        a.status[(size_t)e * N + i] = (uint8_t)st[k];
+        pos_e[i] = p;
+        dir_e[i] = d;
+        st_e[i] = (uint8_t)st[k];
       }
     }
     if (tid == 0) {
       a.agent_pos[e] = ap; a.agent_dir[e] = ad;
-      a.now[e] = now; a.episode[e] = episode; a.overall[e] = overall;
-      a.acc[3 * (size_t)e] = acc_r; a.acc[3 * (size_t)e + 1] = acc_i; a.acc[3 * (size_t)e + 2] = acc_s;
+      a.now[e] = now; a.episode[e] = episode; a.overall[e] += steps_total;
+      if (acc_reset) { a.acc[3 * (size_t)e] = acc_r; a.acc[3 * (size_t)e + 1] = acc_i; a.acc[3 * (size_t)e + 2] = acc_s; }
+      else { a.acc[3 * (size_t)e] += acc_r; a.acc[3 * (size_t)e + 1] += acc_i; a.acc[3 * (size_t)e + 2] += acc_s; }
       if (a.reward) a.reward[e] = reward_sum;
       if (a.terminated) a.terminated[e] = (uint8_t)any_term;
       if (a.truncated) a.truncated[e] = (uint8_t)any_trunc;
     }
+    (void)now_start;
     cta_sync<WARPS>();  // smem tile / scratch reuse by the next environment of this CTA
   }
 }

@@ -211,7 +211,7 @@ struct Tile<double> {
 // The pairwise neighbour-alignment pass [area.py:105-119]: for each of this thread's PPT pedestrians
 // i, sum the unit directions of all slots j with |p_i - p_j|^2 < thr2 (self included).
 // count[] (number of neighbours, area.py:108) is only produced when COUNT is set (fp64 parity mode).
-template <int PPT, bool COUNT>
+template <int PPT, bool COUNT>  // @region pairwise
 __device__ __forceinline__ void pairwise_pass(const Tile<float>& t, int nslots, const float (&xi)[PPT],
                                               const float (&yi)[PPT], float thr2, float (&sx)[PPT], float (&sy)[PPT],
                                               float (&cnt)[PPT]) {
@@ -255,7 +255,7 @@ __device__ __forceinline__ void pairwise_pass(const Tile<float>& t, int nslots, 
   }
 }
 
-template <int PPT, bool COUNT>
+template <int PPT, bool COUNT>  // @region pairwise64
 __device__ __forceinline__ void pairwise_pass(const Tile<double>& t, int nslots, const double (&xi)[PPT],
                                               const double (&yi)[PPT], double thr2, double (&sx)[PPT],
                                               double (&sy)[PPT], double (&cnt)[PPT]) {
@@ -274,7 +274,7 @@ __device__ __forceinline__ void pairwise_pass(const Tile<double>& t, int nslots,
   }
 }
 
-// A one-warp CTA only needs warp-level convergence + memory ordering, not a hardware barrier.
+// A one-warp CTA only needs warp-level convergence + memory ordering, not a hardware barrier.  // @region helpers
 template <int WARPS>
 __device__ __forceinline__ void cta_sync() {
   if constexpr (WARPS == 1) __syncwarp(); else __syncthreads();
@@ -290,7 +290,7 @@ struct RedScratch {
 
 // ------------------------------------------------------------------------------------------
 // Observation encoding of ONE pedestrian row + (thread 0) the agent / exit rows.
-template <typename real>
+template <typename real>  // @region obs
 __device__ __forceinline__ void store_ped_obs(float* __restrict__ row, int i, int N, real px, real py, int st,
                                               float apx, float apy, const KArgs<real>& a) {
   float x = (float)px, y = (float)py;
@@ -386,7 +386,7 @@ __device__ __forceinline__ void store_grav_obs(float* __restrict__ row, float ap
   row[5] = (float)gpy;
 }
 
-// fresh random layout of one pedestrian [pedestrians.py:17-20]
+// fresh random layout of one pedestrian [pedestrians.py:17-20]  // @region reset
 template <typename real>
 __device__ __forceinline__ void random_layout(uint64_t seed, uint32_t env, uint32_t episode, uint32_t ped, real& px,
                                               real& py, real& dx, real& dy) {
@@ -405,7 +405,7 @@ __device__ __forceinline__ void random_layout(uint64_t seed, uint32_t env, uint3
 // PPT pedestrians per thread (pedestrian i = k*THREADS + tid).  N <= 64 runs as ONE WARP per
 // environment (THREADS = 32, PPT = 2): no block barrier, reductions are pure REDUX / shuffles, and
 // the moving pedestrians are compacted (ballot + popc) so the pairwise pass only visits them.
-template <typename real, int THREADS, int PPT>
+template <typename real, int THREADS, int PPT>  // @region load
 __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 ? 16 : 1))) evac_step_kernel(const __grid_constant__ KArgs<real> a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int SLOTS = THREADS * PPT;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
     const float* noise_e = a.noise ? a.noise + (size_t)e * N : nullptr;
     float* obs_e = a.obs ? a.obs + (size_t)e * a.obs_dim : nullptr;
 
-    for (int s = 0; s < a.num_steps; ++s) {
+    for (int s = 0; s < a.num_steps; ++s) {  // @region rng
       // ---------------- Time.step [area.py:53-59]
       const int now_prev = now;
       now += 1; steps_total += 1;
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         else reinterpret_cast<float4*>(noise_s)[b] = make_float4((u01(r.x) - 0.5f) * noise_c, (u01(r.y) - 0.5f) * noise_c,
                                                                  (u01(r.z) - 0.5f) * noise_c, (u01(r.w) - 0.5f) * noise_c);
       }
-      // ---------------- escaped / exiting preparation + source records [area.py:79-101]
+      // ---------------- escaped / exiting preparation + source records [area.py:79-101]  // @region prep
       bool any_fv = false;
       bool efv[PPT];
       real ux[PPT], uy[PPT];
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
           if (so == ST_EXITING) { const real sc = min_(n2 * inv, a.step_size) * inv; dx[k] = vx * sc; dy[k] = vy * sc; }
         }
       }
-      int n_src = N;  // number of source slots the pairwise pass visits
+      int n_src = N;  // number of source slots the pairwise pass visits  // @region compact
       if constexpr (COMPACT) {
         // one warp: rank the moving (exiting / following / viscek) pedestrians and store them densely
         int base = 0;
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         }
       }
       cta_sync<WARPS>();
-      // ---------------- action source + Area.agent_step [area.py:182-210], float32 like the reference
+      // ---------------- action source + Area.agent_step [area.py:182-210], float32 like the reference  // @region agent
       float r_agent = 0.f;
       bool term_agent = false;
       {
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         if (!collide) { ap.x = ptx; ap.y = pty; }
         else { r_agent = -5.f; term_agent = a.term_wall != 0; }
       }
-      // ---------------- pairwise alignment [area.py:105-119]
+      // ---------------- pairwise alignment [area.py:105-119]  // @region pairwise
       real sx[PPT], sy[PPT], cnt[PPT];
       if (__any_sync(0xffffffffu, any_fv)) {
         pairwise_pass<PPT, F64>(tile, n_src, px, py, a.thr2_ped, sx, sy, cnt);
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
 #pragma unroll
         for (int k = 0; k < PPT; ++k) sx[k] = sy[k] = cnt[k] = (real)0;
       }
-      // ---------------- new directions, enslaving, integration, reflection, statuses
+      // ---------------- new directions, enslaving, integration, reflection, statuses  // @region update
       int k_exit = 0, k_fol = 0, n_esc = 0, n_exi = 0, n_fol = 0;
       real sum_dexit = (real)0;
       const real e_adx = (real)__fmul_rn(a.enslaving_f, ad.x), e_ady = (real)__fmul_rn(a.enslaving_f, ad.y);
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         n_esc += (sn_ == ST_ESCAPED); n_exi += (sn_ == ST_EXITING); n_fol += (sn_ == ST_FOLLOWER);
         st[k] = sn_;
       }
-      // ---------------- CTA reduction of counts + intrinsic distance sum
+      // ---------------- CTA reduction of counts + intrinsic distance sum  // @region reduce_reward
       int q0, q1, q2;
       double sd;
       {
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       reward_sum += (float)reward;
       any_term |= terminated; any_trunc |= truncated;
       acc_r += (double)reward; acc_i += (double)intrinsic; acc_s += (double)r_status;
-      // ---------------- same-step auto-reset
+      // ---------------- same-step auto-reset  // @region reset
       if (a.auto_reset && (terminated || truncated)) {
         if (tid == 0) {  // the logging dict of env.py:115-125
           if (!acc_reset) { acc_r += a.acc[3 * (size_t)e]; acc_i += a.acc[3 * (size_t)e + 1]; acc_s += a.acc[3 * (size_t)e + 2]; }
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
           }
         }
       }
-      // ---------------- observation
+      // ---------------- observation  // @region obs
       if (obs_e != nullptr && (a.obs_every_step || s == a.num_steps - 1)) {
         float* row = obs_e + (a.obs_every_step ? (size_t)s * a.E * a.obs_dim : (size_t)0);
         if (a.positions == POS_GRAV) {
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       }
     }  // steps
 
-    // ---------------- write back
+    // ---------------- write back  // @region writeback
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const int i = k * THREADS + tid;
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
   }
 }
 
-// ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------  // @region aux
 // Auxiliary kernel (not on the per-step path): reset / recompute statuses / encode observations.
 // One 128-thread CTA per environment, pedestrians strided over the threads.
 enum { AUX_RESET = 1, AUX_STATUS = 2, AUX_OBS = 4 };

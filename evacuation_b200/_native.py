@@ -10,7 +10,7 @@ import os
 
 from .build import LIB_PATH
 
-EVAC_ABI_VERSION = 1
+EVAC_ABI_VERSION = 2
 NUM_EPISODE_STATS = 9
 EPISODE_STAT_KEYS = (  # env.py:115-125
     "episode_intrinsic_reward", "episode_status_reward", "episode_reward", "episode_length",
@@ -23,6 +23,7 @@ STAT = {"no": 0, "ohe": 1, "cat": 2}
 OBS = {"Dict": 0, "Box": 1}
 PREC = {"fp32": 0, "fp64": 1}
 AGENT = {"table": 0, "random": 1, "rotating": 2}
+SEARCH = {"auto": 0, "brute": 1, "cells": 2}
 
 
 class EvacConfig(C.Structure):
@@ -40,7 +41,7 @@ class EvacConfig(C.Structure):
         ("positions", C.c_int32), ("statuses", C.c_int32), ("obs_type", C.c_int32),
         ("alpha", C.c_double),
         ("to_leader", C.c_double), ("to_pedestrian", C.c_double), ("to_exit", C.c_double), ("to_escape", C.c_double),
-        ("auto_reset", C.c_int32), ("precision", C.c_int32),
+        ("auto_reset", C.c_int32), ("precision", C.c_int32), ("neighbor_search", C.c_int32),
     ]
 
 
@@ -54,6 +55,7 @@ SIGNATURES = {
     "evac_destroy": (C.c_int, [_P]),
     "evac_obs_dim": (C.c_int32, [_P]),
     "evac_num_envs": (C.c_int32, [_P]),
+    "evac_num_cells": (C.c_int32, [_P]),
     "evac_state_elem_size": (C.c_int32, [_P]),
     "evac_reset": (C.c_int, [_P, _P, _P, _P]),
     "evac_set_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),

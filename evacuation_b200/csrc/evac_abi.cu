@@ -59,6 +59,7 @@ struct EvacHandle {
   int64_t launches = 0;
   int threads = 0, ppt = 0;
   int num_sms = 0;
+  int cells_x = 0, cells_y = 0;  // > 0: cell-list neighbour search (multi-warp fp32 shapes)
 };
 
 // smallest double b such that sqrt(v) >= t for every v >= b  <=>  (v < b) == (sqrt(v) < t)
@@ -97,6 +98,9 @@ static KArgs<real> make_args(const EvacHandle* h) {
   a.eps_f = (float)c.eps; a.enslaving_f = (float)c.enslaving_degree;
   a.thr2_ped = thr2_of<real>(c.to_pedestrian); a.thr2_leader = thr2_of<real>(c.to_leader);
   a.thr2_exit = thr2_of<real>(c.to_exit); a.thr2_escape = thr2_of<real>(c.to_escape);
+  a.cells_x = h->cells_x; a.cells_y = h->cells_y;
+  a.cell_inv_x = h->cells_x > 0 ? (float)(h->cells_x / (2.0 * c.width)) : 0.f;
+  a.cell_inv_y = h->cells_y > 0 ? (float)(h->cells_y / (2.0 * c.height)) : 0.f;
   a.exit_reward = c.is_new_exiting_reward; a.follow_reward = c.is_new_followers_reward;
   a.term_wall = c.is_termination_agent_wall_collision;
   a.init_reward = (real)c.init_reward_each_step; a.intrinsic_coef = (real)c.intrinsic_reward_coef;
@@ -120,12 +124,13 @@ static KArgs<real> make_args(const EvacHandle* h) {
 // ------------------------------------------------------------------------------------------
 template <typename real, int THREADS, int PPT>
 static int launch_step_t(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
-  const size_t smem = Tile<real>::bytes(THREADS * PPT) + (size_t)THREADS * PPT * sizeof(float);  // tile + noise
-  static thread_local bool attr_set[16] = {false};
+  size_t smem = Tile<real>::bytes(THREADS * PPT) + (size_t)THREADS * PPT * sizeof(float);  // tile + noise
+  if (a.cells_x > 0) smem += CellSmem::bytes(THREADS * PPT, a.cells_x * a.cells_y);         // + cell list
+  static thread_local size_t attr_set[16] = {0};
   auto kern = evac_step_kernel<real, THREADS, PPT>;
-  if (smem > 48 * 1024 && !attr_set[h->device & 15]) {
+  if (smem > 48 * 1024 && attr_set[h->device & 15] < smem) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[h->device & 15] = true;
+    attr_set[h->device & 15] = smem;
   }
   kern<<<a.E, THREADS, smem, st>>>(a);
   CK(cudaGetLastError());
@@ -191,7 +196,7 @@ int evac_default_config(EvacConfig* c) {
   c->is_termination_agent_wall_collision = 0; c->init_reward_each_step = -1.0; c->max_timesteps = 2000;
   c->positions = EVAC_POS_ABS; c->statuses = EVAC_STAT_NO; c->obs_type = EVAC_OBS_DICT; c->alpha = 3.0;
   c->to_leader = 0.2; c->to_pedestrian = 0.1; c->to_exit = 0.4; c->to_escape = 0.01;  // constants.py:35-38
-  c->auto_reset = 0; c->precision = EVAC_PREC_F32;
+  c->auto_reset = 0; c->precision = EVAC_PREC_F32; c->neighbor_search = EVAC_SEARCH_AUTO;
   return EVAC_OK;
 }
 
@@ -208,6 +213,7 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   if (cfg->positions == EVAC_POS_GRAV && cfg->obs_type == EVAC_OBS_BOX)
     return fail(EVAC_ERR_UNSUPPORTED, "positions='grav' with type='Box' is NotImplementedError in the reference (wrappers/config.py:80-81)");
   if (cfg->precision != EVAC_PREC_F32 && cfg->precision != EVAC_PREC_F64) return fail(EVAC_ERR_INVALID, "invalid precision");
+  if (cfg->neighbor_search < EVAC_SEARCH_AUTO || cfg->neighbor_search > EVAC_SEARCH_CELLS) return fail(EVAC_ERR_INVALID, "invalid neighbor_search");
   if (!(cfg->to_leader > 0 && cfg->to_pedestrian > 0 && cfg->to_exit > 0 && cfg->to_escape > 0))
     return fail(EVAC_ERR_INVALID, "switch distances must be positive");
   if (cfg->max_timesteps < 1) return fail(EVAC_ERR_INVALID, "max_timesteps must be >= 1");
@@ -228,6 +234,13 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   h->obs_dim = compute_obs_dim(*cfg); h->prec = cfg->precision; h->seed = seed; h->env_offset = env_index_offset;
   h->num_sms = prop.multiProcessorCount;
   pick_shape(h->N, &h->threads, &h->ppt);
+  if (h->N > 64 && h->threads > 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search != EVAC_SEARCH_BRUTE) {
+    // cell edge >= (1 + 1e-4) x vision radius: two pedestrians closer than the radius always sit in the same or
+    // in adjacent cells, float32 rounding of the cell index included; at most 64 x 64 cells
+    const double edge = cfg->to_pedestrian * (1.0 + 1e-4);
+    const int gx = (int)fmin(64.0, floor(2.0 * cfg->width / edge)), gy = (int)fmin(64.0, floor(2.0 * cfg->height / edge));
+    if (gx >= 1 && gy >= 1 && (cfg->neighbor_search == EVAC_SEARCH_CELLS || gx * gy >= 16)) { h->cells_x = gx; h->cells_y = gy; }
+  }
   const size_t en = (size_t)h->E * h->N, es = h->prec == EVAC_PREC_F64 ? 16 : 8;
 #define ALLOC(ptr, bytes)                                                      \
   do {                                                                         \
@@ -263,6 +276,7 @@ int evac_destroy(EvacHandle* h) {
 }
 
 int32_t evac_obs_dim(const EvacHandle* h) { return h ? h->obs_dim : -1; }
+int32_t evac_num_cells(const EvacHandle* h) { return h ? h->cells_x * h->cells_y : -1; }
 int32_t evac_num_envs(const EvacHandle* h) { return h ? h->E : -1; }
 int32_t evac_state_elem_size(const EvacHandle* h) { return h ? (h->prec == EVAC_PREC_F64 ? 8 : 4) : -1; }
 int64_t evac_launch_count(const EvacHandle* h) { return h ? h->launches : -1; }

@@ -55,6 +55,10 @@ struct KArgs {
   float width_f, height_f, step_size_f, eps_f, enslaving_f;  // the agent's arithmetic is float32 in the reference
   // thresholds on SQUARED distances, chosen on the host so that (d2 < thr2) == (sqrt(d2) < thr) exactly
   real thr2_ped, thr2_leader, thr2_exit, thr2_escape;
+  // uniform cell grid of the neighbour search (multi-warp shapes, float32): cells_x * cells_y cells of edge
+  // >= vision radius over [-width,width] x [-height,height]; cells_x == 0 -> brute-force tiled pass
+  int cells_x, cells_y;
+  float cell_inv_x, cell_inv_y;  // cells per unit length
   int exit_reward, follow_reward, term_wall;
   real init_reward, intrinsic_coef;
   int max_timesteps;
@@ -180,7 +184,7 @@ struct Tile<float> {
     U2 = P2 + slots / 2 + 1;  // +1: spare look-ahead entry (pairwise_pass)
   }
   static __host__ __device__ constexpr size_t bytes(int slots) { return (size_t)slots * 16 + 32; }
-  __device__ __forceinline__ void put(int j, float x, float y, float ux, float uy) {
+  __device__ __forceinline__ void put(int j, float x, float y, float ux, float uy) const {
     float* p = reinterpret_cast<float*>(P2 + (j >> 1)) + (j & 1);
     float* u = reinterpret_cast<float*>(U2 + (j >> 1)) + (j & 1);
     p[0] = x;
@@ -200,7 +204,7 @@ struct Tile<double> {
     UY = UX + slots;
   }
   static __host__ __device__ constexpr size_t bytes(int slots) { return (size_t)slots * 32; }
-  __device__ __forceinline__ void put(int j, double x, double y, double ux, double uy) {
+  __device__ __forceinline__ void put(int j, double x, double y, double ux, double uy) const {
     X[j] = x;
     Y[j] = y;
     UX[j] = ux;
@@ -270,6 +274,163 @@ __device__ __forceinline__ void pairwise_pass(const Tile<double>& t, int nslots,
       sx[k] += w * ux;
       sy[k] += w * uy;
       cnt[k] += w;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cell-list neighbour search for crowds larger than one warp tile (BASELINE config 4: 4096 pedestrians).
+// [area.py:105-119 computes the full |fv| x |efv| distance matrix; only pairs closer than the vision
+// radius contribute, so binning the sources into a uniform grid of cells with edge >= radius and scanning
+// the 3x3 block of cells around each pedestrian evaluates the SAME predicate on a superset of the
+// contributing pairs.]  All in shared memory, one CTA per environment:
+//   1. histogram of the moving pedestrians over the cells (shared-memory atomics; the returned count is a
+//      provisional, non-deterministic rank)                          2. exclusive scan -> cell_start[]
+//   3. provisional scatter of pedestrian indices                     4. canonical rank = number of
+//      lower-indexed pedestrians of the same cell -> the tile is sorted by (cell, index): the summation
+//      order, hence every float32 result, is deterministic
+//   5. threads walk the SORTED slots (neighbouring lanes sit in the same / adjacent cells: shared-memory
+//      broadcasts, coherent trip counts), three contiguous slot ranges (one per cell row), packed f32x2
+//      pair evaluation like pairwise_pass; result scattered to res[original index]
+//   6. the owner threads read res[] back.
+struct CellSmem {
+  float2* res;           // [SLOTS]  (aliases `list` until step 5)
+  uint16_t* list;        // [SLOTS]  provisional cell lists
+  uint16_t* sorted_idx;  // [SLOTS]  original index | 0x8000 if VISCEK/FOLLOWER
+  int* cell_start;       // [C + 1]
+  int* warp_tot;         // [32]
+  static __host__ __device__ constexpr size_t bytes(int slots, int cells) {
+    return (size_t)slots * 8 + (size_t)slots * 2 + (((size_t)cells + 1 + 3) & ~(size_t)3) * 4 + 32 * 4;
+  }
+  __device__ __forceinline__ CellSmem(unsigned char* base, int slots, int cells) {
+    res = reinterpret_cast<float2*>(base);
+    list = reinterpret_cast<uint16_t*>(base);
+    sorted_idx = reinterpret_cast<uint16_t*>(base + (size_t)slots * 8);
+    cell_start = reinterpret_cast<int*>(base + (size_t)slots * 10);
+    warp_tot = cell_start + ((cells + 1 + 3) & ~3);
+  }
+};
+
+template <typename A>
+__device__ __forceinline__ int cell_of(float x, float y, const A& a, int& cx, int& cy) {
+  cx = min(max((int)((x + a.width_f) * a.cell_inv_x), 0), a.cells_x - 1);  // (int)NaN == 0
+  cy = min(max((int)((y + a.height_f) * a.cell_inv_y), 0), a.cells_y - 1);
+  return cy * a.cells_x + cx;
+}
+
+template <int THREADS, int PPT, typename A>
+__device__ __forceinline__ void cell_list_pass(const Tile<float>& tile, const CellSmem& cs, const A& a, const float (&px)[PPT],
+                                               const float (&py)[PPT], const float (&ux)[PPT], const float (&uy)[PPT],
+                                               const bool (&efv)[PPT], const int (&st)[PPT], float (&sx)[PPT], float (&sy)[PPT]) {
+  constexpr int WARPS = THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = a.cells_x * a.cells_y;
+  // ---- 1. histogram
+  for (int c = tid; c <= C; c += THREADS) cs.cell_start[c] = 0;
+  __syncthreads();
+  int cell[PPT], rank[PPT];
+  bool nan_src = false;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    cell[k] = 0; rank[k] = 0;
+    if (efv[k]) {
+      int cx, cy;
+      cell[k] = cell_of(px[k], py[k], a, cx, cy);
+      rank[k] = atomicAdd(&cs.cell_start[cell[k]], 1);
+      nan_src |= (ux[k] != ux[k]) | (uy[k] != uy[k]);
+    }
+  }
+  // 0 * NaN = NaN: one source without a direction poisons EVERY sum in the reference (area.py:101,118)
+  const bool poisoned = __syncthreads_or(nan_src);
+  // ---- 2. exclusive scan of the C + 1 counters (entry C receives the total)
+  {
+    const int per = (C + THREADS) / THREADS;  // ceil((C + 1) / THREADS)
+    const int lo = min(tid * per, C + 1), hi = min(lo + per, C + 1);
+    int sum = 0;
+    for (int c = lo; c < hi; ++c) sum += cs.cell_start[c];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) cs.warp_tot[warp] = inc;
+    __syncthreads();
+    int off = inc - sum;
+    for (int w = 0; w < warp; ++w) off += cs.warp_tot[w];
+    for (int c = lo; c < hi; ++c) { const int v = cs.cell_start[c]; cs.cell_start[c] = off; off += v; }
+  }
+  __syncthreads();
+  const int n_src = cs.cell_start[C];
+  // ---- 3. provisional scatter
+#pragma unroll
+  for (int k = 0; k < PPT; ++k)
+    if (efv[k]) cs.list[cs.cell_start[cell[k]] + rank[k]] = (uint16_t)(k * THREADS + tid);
+  __syncthreads();
+  // ---- 4. canonical rank inside the cell + final scatter of the source records (tile / sorted_idx do not alias list)
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    if (efv[k]) {
+      const int i = k * THREADS + tid;
+      const int b = cs.cell_start[cell[k]], e = cs.cell_start[cell[k] + 1];
+      int r = b;
+      for (int q = b; q < e; ++q) r += ((int)cs.list[q] < i);
+      const bool fv = (unsigned)(st[k] - ST_VISCEK) <= (unsigned)(ST_FOLLOWER - ST_VISCEK);
+      tile.put(r, px[k], py[k], ux[k], uy[k]);
+      cs.sorted_idx[r] = (uint16_t)(i | (fv ? 0x8000 : 0));
+    }
+  }
+  if (tid < 2) tile.put(n_src + tid, PARK, PARK, 0.f, 0.f);  // pad to an even count (the tile has 2 spare slots)
+  __syncthreads();  // list[] (aliased by res[]) is dead from here on
+  // ---- 5. walk the sorted slots
+  const float thr2 = a.thr2_ped;
+#pragma unroll 1
+  for (int s = tid; s < n_src; s += THREADS) {
+    const int id = cs.sorted_idx[s];
+    if (!(id & 0x8000)) continue;
+    const float4 pp = tile.P2[s >> 1];
+    const float x = (s & 1) ? pp.y : pp.x, y = (s & 1) ? pp.w : pp.z;
+    int cx, cy;
+    cell_of(x, y, a, cx, cy);
+    const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, a.cells_x - 1);
+    const float2 nx = make_float2(-x, -x), ny = make_float2(-y, -y);
+    float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
+    int done = 0;  // even slot index below which everything has been evaluated already
+    for (int row = max(cy - 1, 0); row <= min(cy + 1, a.cells_y - 1); ++row) {
+      const int lo = max(cs.cell_start[row * a.cells_x + cx0] & ~1, done);
+      const int hi = (cs.cell_start[row * a.cells_x + cx1 + 1] + 1) & ~1;
+      int j = lo >> 1;
+      const int je = hi >> 1;
+      if (j < je) {
+        // software pipeline: the operands of the next slot pair are in flight while this one is evaluated
+        // (the look-ahead of the last iteration reads at most the tile's spare entry)
+        float4 p = tile.P2[j], u = tile.U2[j];
+#pragma unroll 2
+        for (; j < je; ++j) {
+          const float4 pn = tile.P2[j + 1], un = tile.U2[j + 1];
+          const float2 dx = __fadd2_rn(make_float2(p.x, p.y), nx);
+          const float2 dy = __fadd2_rn(make_float2(p.z, p.w), ny);
+          float2 d2 = __fmul2_rn(dx, dx);
+          d2 = __ffma2_rn(dy, dy, d2);
+          const float2 w = make_float2(d2.x < thr2 ? 1.f : 0.f, d2.y < thr2 ? 1.f : 0.f);
+          ax = __ffma2_rn(w, make_float2(u.x, u.y), ax);
+          ay = __ffma2_rn(w, make_float2(u.z, u.w), ay);
+          p = pn;
+          u = un;
+        }
+      }
+      done = max(done, hi);
+    }
+    cs.res[id & 0x7fff] = make_float2(ax.x + ax.y, ay.x + ay.y);
+  }
+  __syncthreads();
+  // ---- 6. back to the owners
+  const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    sx[k] = sy[k] = 0.f;
+    const bool fv = (unsigned)(st[k] - ST_VISCEK) <= (unsigned)(ST_FOLLOWER - ST_VISCEK);
+    if (fv) {
+      const float2 r = cs.res[k * THREADS + tid];
+      sx[k] = poisoned ? qnan : r.x;
+      sy[k] = poisoned ? qnan : r.y;
     }
   }
 }
@@ -417,6 +578,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
   __shared__ float2 action_s;
   Tile<real> tile(smem_raw, SLOTS);
   float* noise_s = reinterpret_cast<float*>(smem_raw + Tile<real>::bytes(SLOTS));  // [SLOTS]
+  bool use_cells = false;  // CTA-uniform: cell-list neighbour search instead of the brute-force tiled pass
+  if constexpr (!COMPACT && !F64) use_cells = a.cells_x > 0;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
@@ -510,7 +673,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         }
         n_src = base;
         if (lane < 2) tile.put(base + lane, (real)PARK, (real)PARK, (real)0, (real)0);  // pad to an even count
-      } else {
+      } else if (!use_cells) {
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
           const int i = k * THREADS + tid;
@@ -543,7 +706,16 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       }
       // ---------------- pairwise alignment [area.py:105-119]  // @region pairwise
       real sx[PPT], sy[PPT], cnt[PPT];
-      if (__any_sync(0xffffffffu, any_fv)) {
+      if constexpr (!COMPACT && !F64) {
+        if (use_cells) {
+          const CellSmem cs(smem_raw + Tile<real>::bytes(SLOTS) + (size_t)SLOTS * sizeof(float), SLOTS, a.cells_x * a.cells_y);
+          cell_list_pass<THREADS, PPT>(tile, cs, a, px, py, ux, uy, efv, st, sx, sy);
+        }
+      }
+      if (use_cells) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) cnt[k] = (real)0;
+      } else if (__any_sync(0xffffffffu, any_fv)) {
         pairwise_pass<PPT, F64>(tile, n_src, px, py, a.thr2_ped, sx, sy, cnt);
       } else {
 #pragma unroll

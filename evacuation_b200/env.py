@@ -121,7 +121,7 @@ class EvacuationEnv:
 
     def __init__(self, cfg: EnvConfig, num_envs: int = 1, device=None, seed: int = 0,
                  auto_reset: Optional[bool] = None, precision: str = "fp32", env_index_offset: int = 0,
-                 rng: Optional[str] = None, batched: Optional[bool] = None):
+                 rng: Optional[str] = None, batched: Optional[bool] = None, neighbor_search: str = "auto"):
         if isinstance(cfg, type):  # README.md:72 passes the class itself
             cfg = cfg()
         if precision not in nat.PREC:
@@ -134,6 +134,9 @@ class EvacuationEnv:
             raise ValueError(f"Invalid value of `rng`='{self.rng}'. Must be 'numpy' or 'philox'.")
         self.auto_reset = self.batched if auto_reset is None else bool(auto_reset)
         self.precision = precision
+        if neighbor_search not in nat.SEARCH:
+            raise ValueError(f"Invalid value of `neighbor_search`='{neighbor_search}'. Must be 'auto', 'brute' or 'cells'.")
+        self.neighbor_search = neighbor_search
         self.seed_value = int(seed)
         self.env_index_offset = int(env_index_offset)
         nat.load()  # fail loudly now if the CUDA library is missing
@@ -207,6 +210,7 @@ class EvacuationEnv:
         c.to_exit, c.to_escape = SwitchDistances.to_exit, SwitchDistances.to_escape
         c.auto_reset = int(self.auto_reset)
         c.precision = nat.PREC[self.precision]
+        c.neighbor_search = nat.SEARCH[self.neighbor_search]
         h = C.c_void_p()
         nat.check(lib.evac_create(C.byref(c), self.num_envs, self.device.index, C.c_uint64(self.seed_value),
                                   C.c_int64(self.env_index_offset), C.byref(h)))
@@ -235,6 +239,11 @@ class EvacuationEnv:
             self.close()
         except Exception:
             pass
+
+    @property
+    def num_cells(self) -> int:
+        """Cells of the neighbour-search grid (0 = all-pairs tiles)."""
+        return int(nat.load().evac_num_cells(self._handle()))
 
     @property
     def launch_count(self) -> int:

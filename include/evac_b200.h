@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define EVAC_ABI_VERSION 1
+#define EVAC_ABI_VERSION 2
 
 enum {
   EVAC_OK = 0,
@@ -65,6 +65,10 @@ enum { EVAC_STAT_NO = 0, EVAC_STAT_OHE = 1, EVAC_STAT_CAT = 2 };    /* EnvWrappe
 enum { EVAC_OBS_DICT = 0, EVAC_OBS_BOX = 1 };                       /* EnvWrappersConfig.type      */
 enum { EVAC_PREC_F32 = 0, EVAC_PREC_F64 = 1 };                      /* pedestrian-state arithmetic */
 enum { EVAC_AGENT_TABLE = 0, EVAC_AGENT_RANDOM = 1, EVAC_AGENT_ROTATING = 2 }; /* evac_rollout action source */
+/* neighbour search of the alignment pass (area.py:105-108 builds the full distance matrix):
+ * AUTO = one-warp all-pairs tile for N <= 64, cell list (uniform grid, cell edge >= vision radius) above;
+ * BRUTE = all-pairs shared-memory tiles for every N; CELLS = cell list whenever the shape supports it (N > 64, fp32) */
+enum { EVAC_SEARCH_AUTO = 0, EVAC_SEARCH_BRUTE = 1, EVAC_SEARCH_CELLS = 2 };
 
 /* Number of floats in one episode-statistics record, in the key order of env.py:115-125:
  * episode_intrinsic_reward, episode_status_reward, episode_reward, episode_length,
@@ -99,6 +103,7 @@ typedef struct EvacConfig {
   int32_t auto_reset; /* 1: an env that terminates/truncates is reset inside the same step
                          (gymnasium vector-env "same-step" semantics, rpo_agent.py:193-203) */
   int32_t precision;  /* EVAC_PREC_F32 (product) or EVAC_PREC_F64 (parity mode) */
+  int32_t neighbor_search; /* EVAC_SEARCH_* */
 } EvacConfig;
 
 typedef struct EvacHandle EvacHandle;
@@ -120,6 +125,8 @@ int evac_destroy(EvacHandle* h);
  *   grav : [agent(2) | grad_potential_exit(2) | grad_potential_pedestrians(2)] */
 int32_t evac_obs_dim(const EvacHandle* h);
 int32_t evac_num_envs(const EvacHandle* h);
+/* number of cells of the neighbour-search grid (0 = all-pairs tiles) */
+int32_t evac_num_cells(const EvacHandle* h);
 /* bytes per element of the pedestrian state arrays exchanged by get/set_state (4 or 8) */
 int32_t evac_state_elem_size(const EvacHandle* h);
 

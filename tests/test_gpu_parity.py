@@ -187,14 +187,19 @@ def test_free_running_episode_parity(name):
 @pytest.mark.parametrize("n,num_envs,steps", [(1, 7, 3), (2, 5, 3), (31, 3, 3), (32, 3, 3), (64, 4, 3), (65, 3, 2), (128, 2, 2), (129, 2, 2),
                                               (257, 2, 2), (600, 2, 2), (1500, 1, 1), (4096, 1, 1)])
 @pytest.mark.parametrize("wrap", [dict(positions="rel", statuses="ohe", type="Box"), dict(positions="grav", alpha=2)])
-def test_kernel_shapes_random_states(n, num_envs, steps, wrap):
-    """All CTA shapes (THREADS x PPT), ragged N, random layouts: teacher-forced against the oracle."""
+@pytest.mark.parametrize("search", ["auto", "brute"])
+def test_kernel_shapes_random_states(n, num_envs, steps, wrap, search):
+    """All CTA shapes (THREADS x PPT), ragged N, random layouts, both neighbour searches (N > 64: "auto" = cell
+    list, "brute" = all-pairs tiles): teacher-forced against the oracle."""
+    if n <= 64 and search == "brute":
+        pytest.skip("N <= 64 always runs the one-warp all-pairs tile")
     rs = np.random.RandomState(n)
     env_kw = dict(number_of_pedestrians=n, is_new_exiting_reward=True, intrinsic_reward_coef=0.3, enslaving_degree=0.7)
     cfg = OracleConfig(**env_kw, **wrap)
-    env = _make_env(env_kw, wrap, num_envs)
+    env = _make_env(env_kw, wrap, num_envs, neighbor_search=search)
     u = env.unwrapped
     u.reset()
+    assert (u.num_cells > 0) == (n > 64 and search == "auto")
     oracles = []
     for e in range(num_envs):
         o = OracleEnv(cfg)
@@ -225,6 +230,78 @@ def test_kernel_shapes_random_states(n, num_envs, steps, wrap):
             _assert_close("directions", st["directions"][e].cpu().numpy() * alive, o.directions * alive, scale=0.01, ill_conditioned=5e-2)
             _assert_close("reward", reward[e].item(), r)
             _assert_obs_close(wrap, flat[e], flatten_observation(oobs), rtol=5e-5)
+
+
+@pytest.mark.parametrize("n,width,height,vision", [(4096, 1.0, 1.0, 0.1), (1000, 1.5, 0.8, 0.1), (300, 1.0, 1.0, 0.35), (2048, 1.0, 1.0, 0.011), (200, 1.0, 1.0, 0.9),
+                                                   (500, 0.3, 0.3, 0.1)])
+def test_cell_list_equals_all_pairs_search(n, width, height, vision, monkeypatch):
+    """Large crowds (BASELINE config 4): the cell-list neighbour search evaluates the same predicate on a superset
+    of the contributing pairs, so a free-running rollout must retrace the all-pairs kernel (only the float32
+    summation order differs).  Includes a dense cluster (hundreds of pedestrians in one cell), non-square arenas,
+    a grid that hits the 64 x 64 cap, a 2 x 2 grid, and run-to-run determinism of the shared-memory-atomic build."""
+    import evacuation_b200 as eb
+
+    monkeypatch.setattr(eb.SwitchDistances, "to_pedestrian", vision)
+    E, steps = 3, 12
+    env_kw = dict(number_of_pedestrians=n, width=width, height=height, is_new_exiting_reward=True, intrinsic_reward_coef=0.3,
+                  enslaving_degree=0.6, noise_coef=0.4)
+    wrap = dict(positions="rel", statuses="ohe", type="Box")
+    rs = np.random.RandomState(n)
+    pos = rs.uniform(-1, 1, (E, n, 2)) * np.array([width, height])
+    pos[1, : n // 2] = np.array([0.3 * width, -0.2 * height]) + rs.normal(0, 0.03, (n // 2, 2))  # dense cluster
+    pos = np.clip(pos, [-width, -height], [width, height])
+    ang = rs.uniform(0, 2 * np.pi, (E, n))
+    dirs = np.stack([np.cos(ang), np.sin(ang)], axis=-1)
+    actions = rs.uniform(-1, 1, (steps, E, 2)).astype(np.float32)
+    noise = rs.uniform(-0.2, 0.2, (steps, E, n)).astype(np.float32)
+    out = {}
+    for key, search in (("cells", "cells"), ("cells2", "cells"), ("brute", "brute")):
+        env = _make_env(env_kw, wrap, E, neighbor_search=search)
+        u = env.unwrapped
+        u.reset()
+        assert (u.num_cells > 0) == (search == "cells")
+        u.set_state(positions=pos, directions=dirs, agent_position=np.zeros((E, 2), np.float32), agent_direction=np.zeros((E, 2), np.float32),
+                    now=np.zeros(E, np.int32))
+        rew = []
+        for s in range(steps):
+            obs, r, _, _, _ = env.step(torch.as_tensor(actions[s]), noise=torch.as_tensor(noise[s]))
+            rew.append(r.cpu().numpy().copy())
+        st = u.get_state()
+        out[key] = dict(pos=st["positions"].cpu().numpy(), dir=st["directions"].cpu().numpy(), st=st["statuses"].cpu().numpy(),
+                        rew=np.array(rew), obs=obs.cpu().numpy().copy())
+        u.close()
+    for k in ("pos", "dir", "st", "rew", "obs"):  # deterministic: identical bits run to run
+        assert np.array_equal(out["cells"][k], out["cells2"][k], equal_nan=True), k
+    assert (out["cells"]["st"] != out["brute"]["st"]).sum() <= 2
+    # (an ill-conditioned sum -- neighbours nearly cancelling -- turns a 1-ulp difference of the sum into a visible angle)
+    assert np.abs(out["cells"]["pos"] - out["brute"]["pos"]).max() <= 5e-4
+    close = np.abs(out["cells"]["pos"] - out["brute"]["pos"]) <= 1e-6
+    assert close.mean() >= 0.999
+    np.testing.assert_allclose(out["cells"]["rew"], out["brute"]["rew"], rtol=1e-4, atol=1e-4)
+
+
+def test_cell_list_nan_poisoning_matches_all_pairs():
+    """A zero direction (0/0 = NaN unit vector, area.py:101) poisons EVERY neighbour sum in the reference; the cell
+    list must reproduce that, not only for the pedestrians whose cells contain the NaN source."""
+    n, E = 300, 2
+    env_kw = dict(number_of_pedestrians=n)
+    wrap = dict(positions="abs", statuses="no", type="Dict")
+    rs = np.random.RandomState(5)
+    pos = rs.uniform(-1, 1, (E, n, 2))
+    pos[:, :, 1] = np.abs(pos[:, :, 1]) * 0.9 + 0.05  # nobody near the exit
+    ang = rs.uniform(0, 2 * np.pi, (E, n))
+    dirs = np.stack([np.cos(ang), np.sin(ang)], axis=-1)
+    dirs[1, 7] = 0.0
+    res = {}
+    for search in ("cells", "brute"):
+        env = _make_env(env_kw, wrap, E, neighbor_search=search)
+        u = env.unwrapped
+        u.reset()
+        u.set_state(positions=pos, directions=dirs, agent_position=np.full((E, 2), 0.9, np.float32))
+        env.step(torch.zeros((E, 2)) + 0.1, noise=torch.zeros((E, n)))
+        res[search] = u.get_state()["positions"].cpu().numpy()
+    assert np.array_equal(np.isnan(res["cells"]), np.isnan(res["brute"]))
+    assert not np.isnan(res["cells"][0]).any() and np.isnan(res["cells"][1]).sum() >= 2 * (n - 1)
 
 
 def test_kat0_through_the_drop_in_api():

@@ -12,6 +12,7 @@
 
 #include "../../include/evac_b200.h"
 #include "evac_kernels.cuh"
+#include "evac_warp.cuh"
 
 using namespace evac;
 
@@ -60,6 +61,7 @@ struct EvacHandle {
   int threads = 0, ppt = 0;
   int num_sms = 0;
   int cells_x = 0, cells_y = 0;  // > 0: cell-list neighbour search (multi-warp fp32 shapes)
+  bool warp_kernel = true;       // N <= 64 fp32: evac_warp_kernel (false: the generic kernel, EVAC_WARP_KERNEL=generic)
 };
 
 // smallest double b such that sqrt(v) >= t for every v >= b  <=>  (v < b) == (sqrt(v) < t)
@@ -124,7 +126,7 @@ static KArgs<real> make_args(const EvacHandle* h) {
 // ------------------------------------------------------------------------------------------
 template <typename real, int THREADS, int PPT>
 static int launch_step_t(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
-  size_t smem = Tile<real>::bytes(THREADS * PPT) + (size_t)THREADS * PPT * sizeof(float);  // tile + noise
+  size_t smem = Tile<real>::bytes(THREADS * PPT);                                           // source tile
   if (a.cells_x > 0) smem += CellSmem::bytes(THREADS * PPT, a.cells_x * a.cells_y);         // + cell list
   static thread_local size_t attr_set[16] = {0};
   auto kern = evac_step_kernel<real, THREADS, PPT>;
@@ -150,8 +152,22 @@ static void pick_shape(int n, int* threads, int* ppt) {
   else { *threads = 1024; *ppt = 4; }
 }
 
+// N <= 64, float32: the dedicated one-warp kernel (evac_warp.cuh), observation encoding resolved at compile time.
+// EVAC_WARP_KERNEL=generic selects evac_step_kernel<float,32,2> instead (A/B measurements).
+static int launch_warp(EvacHandle* h, const KArgs<float>& a, cudaStream_t st) {
+  if (a.positions == POS_REL && a.statuses == STAT_OHE && a.obs_type == OBS_BOX) evac_warp_kernel<WMODE_REL_OHE_BOX><<<a.E, 32, 0, st>>>(a);
+  else if (a.positions == POS_GRAV) evac_warp_kernel<WMODE_GRAV><<<a.E, 32, 0, st>>>(a);
+  else evac_warp_kernel<WMODE_GENERIC><<<a.E, 32, 0, st>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return EVAC_OK;
+}
+
 template <typename real>
 static int launch_step(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
+  if constexpr (std::is_same<real, float>::value) {
+    if (h->threads == 32 && h->warp_kernel) return launch_warp(h, a, st);
+  }
   switch (h->threads * 16 + h->ppt) {
     case 32 * 16 + 2: return launch_step_t<real, 32, 2>(h, a, st);
     case 64 * 16 + 1: return launch_step_t<real, 64, 1>(h, a, st);
@@ -216,7 +232,7 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   if (cfg->neighbor_search < EVAC_SEARCH_AUTO || cfg->neighbor_search > EVAC_SEARCH_CELLS) return fail(EVAC_ERR_INVALID, "invalid neighbor_search");
   if (!(cfg->to_leader > 0 && cfg->to_pedestrian > 0 && cfg->to_exit > 0 && cfg->to_escape > 0))
     return fail(EVAC_ERR_INVALID, "switch distances must be positive");
-  if (cfg->max_timesteps < 1) return fail(EVAC_ERR_INVALID, "max_timesteps must be >= 1");
+  if (cfg->max_timesteps < 1 || cfg->max_timesteps > (1 << 21)) return fail(EVAC_ERR_INVALID, "max_timesteps must be in 1 .. 2^21 (the step index is a 21-bit field of the Philox counter)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -234,6 +250,7 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   h->obs_dim = compute_obs_dim(*cfg); h->prec = cfg->precision; h->seed = seed; h->env_offset = env_index_offset;
   h->num_sms = prop.multiProcessorCount;
   pick_shape(h->N, &h->threads, &h->ppt);
+  { const char* wk = getenv("EVAC_WARP_KERNEL"); h->warp_kernel = !(wk && strcmp(wk, "generic") == 0); }
   if (h->N > 64 && h->threads > 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search != EVAC_SEARCH_BRUTE) {
     // cell edge >= (1 + 1e-4) x vision radius: two pedestrians closer than the radius always sit in the same or
     // in adjacent cells, float32 rounding of the cell index included; at most 64 x 64 cells

@@ -575,18 +575,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
   using real2 = typename vec2<real>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ RedScratch<WARPS> red_a, red_b;
-  __shared__ float2 action_s;
   Tile<real> tile(smem_raw, SLOTS);
-  float* noise_s = reinterpret_cast<float*>(smem_raw + Tile<real>::bytes(SLOTS));  // [SLOTS]
   bool use_cells = false;  // CTA-uniform: cell-list neighbour search instead of the brute-force tiled pass
   if constexpr (!COMPACT && !F64) use_cells = a.cells_x > 0;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const int n_blocks = (N + 3) >> 2;                                            // Philox blocks of noise
-  const int n_rng = (a.noise == nullptr ? n_blocks : 0);
-  const int n_rng_all = n_rng + (a.agent_kind == AGENT_RANDOM ? 1 : 0);         // + one block for the RandomAgent
   const float noise_c = (float)a.noise_coef;
 
   for (int e = blockIdx.x; e < a.E; e += gridDim.x) {
@@ -626,16 +621,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       const int now_prev = now;
       now += 1; steps_total += 1;
       const bool truncated = now >= a.max_timesteps;
-      // ---------------- random streams for this step: one Philox4x32-10 block serves FOUR pedestrians
-      // (noise of pedestrian i = word i&3 of block i>>2), computed once per block and shared through smem;
-      // the RandomAgent action (action_space.sample() ~ U[-1,1)^2) is one more block of the same pass.
-      for (int b = tid; b < n_rng_all; b += THREADS) {
-        const bool is_action = (b >= n_rng);
-        const Philox4 r = evac_random(a.seed, is_action ? STREAM_AGENT : STREAM_NOISE, env_g, (uint32_t)episode,
-                                      (uint32_t)now_prev, is_action ? 0u : (uint32_t)b);
-        if (is_action) action_s = make_float2(2.f * u01(r.x) - 1.f, 2.f * u01(r.y) - 1.f);
-        else reinterpret_cast<float4*>(noise_s)[b] = make_float4((u01(r.x) - 0.5f) * noise_c, (u01(r.y) - 0.5f) * noise_c,
-                                                                 (u01(r.z) - 0.5f) * noise_c, (u01(r.w) - 0.5f) * noise_c);
+      // ---------------- random streams of this step (Philox2x32-10, philox.cuh): the RandomAgent action
+      // (action_space.sample() ~ U[-1,1)^2) is computed redundantly by every thread; the noise words are drawn where used
+      float2 action_r = make_float2(0.f, 0.f);
+      if (a.agent_kind == AGENT_RANDOM) {
+        const uint2 r = evac_agent_block(a.seed, env_g, (uint32_t)episode, (uint32_t)now_prev);
+        action_r = make_float2(2.f * u01(r.x) - 1.f, 2.f * u01(r.y) - 1.f);
       }
       // ---------------- escaped / exiting preparation + source records [area.py:79-101]  // @region prep
       bool any_fv = false;
@@ -691,7 +682,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
           const float2 av = a.actions[(size_t)s * a.E + e];
           ax = av.x; ay = av.y;
         } else if (a.agent_kind == AGENT_RANDOM) {
-          ax = action_s.x; ay = action_s.y;
+          ax = action_r.x; ay = action_r.y;
         } else {  // RotatingAgent [rotating_agent.py:12-16]
           const float ph = 0.05f * (float)now;
           ax = sinf(ph); ay = cosf(ph);
@@ -708,7 +699,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       real sx[PPT], sy[PPT], cnt[PPT];
       if constexpr (!COMPACT && !F64) {
         if (use_cells) {
-          const CellSmem cs(smem_raw + Tile<real>::bytes(SLOTS) + (size_t)SLOTS * sizeof(float), SLOTS, a.cells_x * a.cells_y);
+          const CellSmem cs(smem_raw + Tile<real>::bytes(SLOTS), SLOTS, a.cells_x * a.cells_y);
           cell_list_pass<THREADS, PPT>(tile, cs, a, px, py, ux, uy, efv, st, sx, sy);
         }
       }
@@ -731,7 +722,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         const int so = st[k];
         const bool fv = (unsigned)(so - ST_VISCEK) <= (unsigned)(ST_FOLLOWER - ST_VISCEK);
         if (fv) {
-          const float nzf = noise_e ? noise_e[((size_t)s * a.E) * N + i] : noise_s[i];
+          float nzf;
+          if (noise_e) {
+            nzf = noise_e[((size_t)s * a.E) * N + i];
+          } else {
+            const uint2 r = evac_noise_block(a.seed, env_g, (uint32_t)episode, (uint32_t)now_prev, evac_noise_block_of((uint32_t)i));
+            nzf = (u01(evac_noise_word_of((uint32_t)i) ? r.y : r.x) - 0.5f) * noise_c;
+          }
           if constexpr (F64) {  // literal transcription of area.py:108-133
             const double n = fmax(1.0, cnt[k]);
             const double th = atan2(sy[k] / n, sx[k] / n) + (double)nzf;

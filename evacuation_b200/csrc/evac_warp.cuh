@@ -1,0 +1,287 @@
+// One-warp-per-environment fused step kernel for N <= 64 pedestrians, float32 (the BASELINE headline
+// shapes: 60 pedestrians).  Same semantics as evac_step_kernel (evac_kernels.cuh; reference file:line
+// citations there and inline below) but written as straight-line warp code:
+//   * lane L owns pedestrians L and L + 32; every per-pedestrian quantity is kept as an (x, y) float2 so the
+//     epilogue arithmetic runs on Blackwell's packed FP32 instructions (FADD2 / FMUL2 / FFMA2) exactly like the
+//     pairwise pass -- one instruction per pedestrian instead of one per component;
+//   * the observation encoding is a template parameter (no per-step mode branches), all loads of a step are
+//     issued up front (incl. the read-modify-write words of lane 0), reductions are one REDUX + one shuffle tree;
+//   * the angular noise is one Philox2x32-10 block per lane (two words = the lane's two pedestrians), no
+//     shared-memory staging; no block barrier anywhere (one warp: __syncwarp only).
+#pragma once
+#include "evac_kernels.cuh"
+
+namespace evac {
+
+enum { WMODE_GENERIC = 0, WMODE_REL_OHE_BOX = 1, WMODE_GRAV = 2 };
+
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
+// per-pedestrian working set of the warp kernel
+struct WPed {
+  float2 p, d;  // position, direction
+  int st;       // status (ST_NONE for padding lanes)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
+  __shared__ __align__(16) float4 tile_s[66];  // Tile<float> of 64 slots (+ the look-ahead entries)
+  const Tile<float> tile(reinterpret_cast<unsigned char*>(tile_s), 64);
+  const int lane = threadIdx.x, e = blockIdx.x, N = a.N;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const bool valid[2] = {lane < N, lane + 32 < N};
+  const uint32_t env_g = (uint32_t)(a.env_offset + e);
+  const float2 exit_p = make_float2(0.f, -1.f);  // area.py:36-39
+
+  // ---------------- load state: everything this launch reads is requested before anything is used
+  float2* __restrict__ pos_e = a.pos + (size_t)e * N;
+  float2* __restrict__ dir_e = a.dir + (size_t)e * N;
+  uint8_t* __restrict__ st_e = a.status + (size_t)e * N;
+  WPed q[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    q[k].p = q[k].d = make_float2(0.f, 0.f);
+    q[k].st = ST_NONE;
+    if (valid[k]) {
+      q[k].p = pos_e[lane + 32 * k];
+      q[k].d = dir_e[lane + 32 * k];
+      q[k].st = st_e[lane + 32 * k];
+    }
+  }
+  float2 ap = a.agent_pos[e], ad = a.agent_dir[e];
+  int now = a.now[e];
+  int episode = a.episode[e];
+  long long overall = 0;
+  double acc_r = 0, acc_i = 0, acc_s = 0;  // lane 0: the episode accumulators of env.py:168-170
+  if (lane == 0) {
+    overall = a.overall[e];
+    acc_r = a.acc[3 * (size_t)e]; acc_i = a.acc[3 * (size_t)e + 1]; acc_s = a.acc[3 * (size_t)e + 2];
+  }
+  float reward_sum = 0.f;
+  int any_term = 0, any_trunc = 0;
+  const float noise_c = a.noise_coef;
+  const float* noise_e = a.noise ? a.noise + (size_t)e * N : nullptr;
+  float* obs_e = a.obs ? a.obs + (size_t)e * a.obs_dim : nullptr;
+  const float2 wall = make_float2(a.width, a.height);
+
+  for (int s = 0; s < a.num_steps; ++s) {  // @region wrng
+    // ---------------- Time.step [area.py:53-59]
+    const int now_prev = now;
+    now += 1;
+    const bool truncated = now >= a.max_timesteps;
+    // ---------------- angular noise of this lane's two pedestrians [area.py:124]
+    float nz[2];
+    if (noise_e != nullptr) {
+      const float* np_ = noise_e + (size_t)s * a.E * N;
+      nz[0] = valid[0] ? np_[lane] : 0.f;
+      nz[1] = valid[1] ? np_[lane + 32] : 0.f;
+    } else {
+      const uint2 r = evac_noise_block(a.seed, env_g, (uint32_t)episode, (uint32_t)now_prev, (uint32_t)lane);
+      nz[0] = (u01(r.x) - 0.5f) * noise_c;
+      nz[1] = (u01(r.y) - 0.5f) * noise_c;
+    }
+    // ---------------- escaped / exiting preparation + unit directions [area.py:79-101]  // @region wprep
+    float2 u[2];
+    bool efv[2], fv[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int so = q[k].st;
+      if (so == ST_ESCAPED) { q[k].d = make_float2(0.f, 0.f); q[k].p = exit_p; }
+      float2 v = q[k].d;
+      if (so == ST_EXITING) v = __fadd2_rn(exit_p, make_float2(-q[k].p.x, -q[k].p.y));
+      efv[k] = (unsigned)(so - ST_VISCEK) <= (unsigned)(ST_EXITING - ST_VISCEK);
+      fv[k] = (unsigned)(so - ST_VISCEK) <= (unsigned)(ST_FOLLOWER - ST_VISCEK);
+      // u = v / |v|; a zero direction gives NaN exactly like area.py:101
+      const float2 sq = __fmul2_rn(v, v);
+      const float n2 = sq.x + sq.y;
+      const float inv = inv_norm(n2);
+      u[k] = __fmul2_rn(v, splat(inv));
+      if (so == ST_EXITING) q[k].d = __fmul2_rn(v, splat(fminf(n2 * inv, a.step_size) * inv));  // dir = u * min(|v|, step)
+    }
+    // ---------------- compact the moving pedestrians into the shared tile  // @region wcompact
+    int n_src;
+    {
+      const uint32_t m0 = __ballot_sync(0xffffffffu, efv[0]), m1 = __ballot_sync(0xffffffffu, efv[1]);
+      const int c0 = __popc(m0);
+      if (efv[0]) tile.put(__popc(m0 & lt_mask), q[0].p.x, q[0].p.y, u[0].x, u[0].y);
+      if (efv[1]) tile.put(c0 + __popc(m1 & lt_mask), q[1].p.x, q[1].p.y, u[1].x, u[1].y);
+      n_src = c0 + __popc(m1);
+      if (lane < 2) tile.put(n_src + lane, PARK, PARK, 0.f, 0.f);  // pad to an even count
+    }
+    __syncwarp();
+    // ---------------- action source + Area.agent_step [area.py:182-210], IEEE float32 like the reference  // @region wagent
+    float r_agent = 0.f;
+    bool term_agent = false;
+    {
+      float ax, ay;
+      if (a.agent_kind == AGENT_TABLE) {
+        const float2 av = a.actions[(size_t)s * a.E + e];
+        ax = av.x; ay = av.y;
+      } else if (a.agent_kind == AGENT_RANDOM) {  // RandomAgent: action_space.sample() ~ U[-1,1)^2 [random_agent.py:8-9]
+        const uint2 r = evac_agent_block(a.seed, env_g, (uint32_t)episode, (uint32_t)now_prev);
+        ax = 2.f * u01(r.x) - 1.f; ay = 2.f * u01(r.y) - 1.f;
+      } else {  // RotatingAgent [rotating_agent.py:12-16]
+        const float ph = 0.05f * (float)now;
+        ax = sinf(ph); ay = cosf(ph);
+      }
+      const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay))), a.eps_f);
+      ax = __fdiv_rn(ax, nrm); ay = __fdiv_rn(ay, nrm);
+      ad.x = __fmul_rn(a.step_size_f, ax); ad.y = __fmul_rn(a.step_size_f, ay);
+      const float ptx = __fadd_rn(ap.x, ad.x), pty = __fadd_rn(ap.y, ad.y);
+      const bool collide = (ptx < -a.width_f) | (ptx > a.width_f) | (pty < -a.height_f) | (pty > a.height_f);
+      if (!collide) { ap.x = ptx; ap.y = pty; }
+      else { r_agent = -5.f; term_agent = a.term_wall != 0; }
+    }
+    // ---------------- pairwise alignment [area.py:105-119]  // @region wpairwise
+    float sx[2], sy[2], cnt[2];
+    {
+      const float xi[2] = {q[0].p.x, q[1].p.x}, yi[2] = {q[0].p.y, q[1].p.y};
+      if (__any_sync(0xffffffffu, fv[0] | fv[1])) pairwise_pass<2, false>(tile, n_src, xi, yi, a.thr2_ped, sx, sy, cnt);
+      else sx[0] = sx[1] = sy[0] = sy[1] = 0.f;
+    }
+    // ---------------- new headings, enslaving, integration, reflection, statuses  // @region wupdate
+    const float2 e_ad = make_float2(__fmul_rn(a.enslaving_f, ad.x), __fmul_rn(a.enslaving_f, ad.y));  // float32 like area.py:140
+    int counts = 0;  // k_exit | k_fol << 8 | n_esc << 16 | n_exi << 24   (each <= 64)
+    float sum_dexit = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int so = q[k].st;
+      if (fv[k]) {
+        // cos/sin(atan2(my, mx) + nz) == unit(m) rotated by nz; atan2(0, 0) = 0 -> unit = (1, 0)  [area.py:120-136]
+        const float m2 = fmaf(sx[k], sx[k], sy[k] * sy[k]);
+        float2 c = make_float2(1.f, 0.f);
+        if (m2 != 0.f) c = __fmul2_rn(make_float2(sx[k], sy[k]), splat(inv_norm(m2)));
+        float sn, cn;
+        sincos_noise(nz[k], sn, cn);
+        float2 nd = __fmul2_rn(splat(c.x), make_float2(cn, sn));
+        nd = __ffma2_rn(make_float2(-c.y, c.y), make_float2(sn, cn), nd);
+        nd = __fmul2_rn(nd, splat(a.step_size));
+        if (so == ST_FOLLOWER) nd = __ffma2_rn(splat(a.one_minus_enslaving), nd, e_ad);  // area.py:138-142
+        q[k].d = nd;
+      }
+      if (efv[k]) q[k].p = __fadd2_rn(q[k].p, q[k].d);
+      {  // wall reflection for ALL pedestrians [area.py:147-152]
+        const float2 cl = make_float2(fminf(fmaxf(q[k].p.x, -wall.x), wall.x), fminf(fmaxf(q[k].p.y, -wall.y), wall.y));
+        const float2 miss = __fadd2_rn(q[k].p, make_float2(-cl.x, -cl.y));
+        q[k].p = __ffma2_rn(splat(-2.f), miss, q[k].p);
+        if (miss.x != 0.f) q[k].d.x = -q[k].d.x;
+        if (miss.y != 0.f) q[k].d.y = -q[k].d.y;
+      }
+      // statuses: a pure function of (position, agent position) [statuses.py:29-48]
+      const float2 da = __fadd2_rn(make_float2(ap.x, ap.y), make_float2(-q[k].p.x, -q[k].p.y));
+      const float2 de = __fadd2_rn(exit_p, make_float2(-q[k].p.x, -q[k].p.y));
+      const float da2 = fmaf(da.x, da.x, da.y * da.y), de2 = fmaf(de.x, de.x, de.y * de.y);
+      int sn_ = ST_VISCEK;
+      if (da2 < a.thr2_leader) sn_ = ST_FOLLOWER;
+      if (de2 < a.thr2_exit) sn_ = ST_EXITING;
+      if (de2 < a.thr2_escape) sn_ = ST_ESCAPED;
+      if (valid[k]) {
+        sum_dexit += sqrt_fast(de2);
+        counts += (int)(fv[k] && sn_ == ST_EXITING) + ((int)(so == ST_VISCEK && sn_ == ST_FOLLOWER) << 8) +
+                  ((int)(sn_ == ST_ESCAPED) << 16) + ((int)(sn_ == ST_EXITING) << 24);
+        q[k].st = sn_;
+      }
+    }
+    // ---------------- warp reduction, rewards, termination [reward.py:19-46, area.py:174-180, env.py:158-171]  // @region wreward
+    counts = __reduce_add_sync(0xffffffffu, counts);
+    const float sd = warp_sum(sum_dexit);
+    const int K_exit = counts & 0xff, K_fol = (counts >> 8) & 0xff, N_esc = (counts >> 16) & 0xff, N_exi = (counts >> 24) & 0xff;
+    const float tf = 1.f - (float)now * a.inv_200n, intrinsic = 0.f - sd * a.inv_n;
+    float r_ped = a.init_reward;
+    if (a.exit_reward) r_ped += (15.f + 10.f * tf) * (float)K_exit;
+    if (a.follow_reward) r_ped += (10.f + 5.f * tf) * (float)K_fol;
+    const float r_status = r_agent + r_ped;
+    const float reward = r_status + a.intrinsic_coef * intrinsic;
+    const bool terminated = term_agent || (N_esc == N);
+    reward_sum += reward;
+    any_term |= terminated; any_trunc |= truncated;
+    acc_r += (double)reward; acc_i += (double)intrinsic; acc_s += (double)r_status;
+    overall += 1;
+    // ---------------- same-step auto-reset (gymnasium vector-env semantics)  // @region wreset
+    if (a.auto_reset && (terminated || truncated)) {
+      const int N_fol = __popc(__ballot_sync(0xffffffffu, q[0].st == ST_FOLLOWER)) + __popc(__ballot_sync(0xffffffffu, q[1].st == ST_FOLLOWER));
+      if (lane == 0) {  // the logging dict of env.py:115-125
+        float* es = a.ep_stats + (size_t)e * NUM_EPISODE_STATS;
+        const float v[NUM_EPISODE_STATS] = {(float)acc_i, (float)acc_s, (float)acc_r, (float)now, (float)N_esc, (float)N_exi,
+                                            (float)N_fol, (float)(N - N_esc - N_exi - N_fol), (float)overall};
+#pragma unroll
+        for (int t = 0; t < NUM_EPISODE_STATS; ++t) { es[t] = v[t]; atomicAdd(a.totals + 1 + t, (double)v[t]); }
+        atomicAdd(a.totals, 1.0);
+        a.ep_finished[e] = 1;
+      }
+      acc_r = acc_i = acc_s = 0;
+      now = 0; episode += 1;
+      ap = make_float2(0.f, 0.f); ad = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (valid[k]) {
+          float dummy;
+          random_layout<float>(a.seed, env_g, (uint32_t)episode, (uint32_t)(lane + 32 * k), q[k].p.x, q[k].p.y, q[k].d.x, q[k].d.y);
+          q[k].st = status_of<float>(q[k].p.x, q[k].p.y, 0.f, 0.f, a, dummy);
+        }
+      }
+    }
+    // ---------------- observation [wrappers.py:8-96, gravity_encoding.py:8-81]  // @region wobs
+    if (obs_e != nullptr && (a.obs_every_step || s == a.num_steps - 1)) {
+      float* row = obs_e + (a.obs_every_step ? (size_t)s * a.E * a.obs_dim : (size_t)0);
+      if constexpr (MODE == WMODE_REL_OHE_BOX) {
+        // rows = [agent; exit; pedestrians], cols = [x, y, ohe(4)]; relative positions / sqrt(2) (float32 hypotenuse)
+        const float inv_hyp = (float)(1.0 / 1.41421353816986083984375);
+        const float2 nap = make_float2(-ap.x, -ap.y);
+        if (lane == 0) {
+          const float2 ex = __fmul2_rn(__fadd2_rn(exit_p, nap), splat(inv_hyp));
+          float2* r = reinterpret_cast<float2*>(row);  // rows of 24 (N + 2) bytes: 8-byte aligned for every N
+          r[0] = ap; r[1] = make_float2(0.f, 0.f); r[2] = make_float2(0.f, 0.f);  // agent row, status [0,0,0,0]
+          r[3] = ex; r[4] = make_float2(1.f, 0.f); r[5] = make_float2(0.f, 0.f);  // exit row,  status [1,0,0,0]
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (valid[k]) {
+            float2* r = reinterpret_cast<float2*>(row + (lane + 32 * k + 2) * 6);
+            const int st = q[k].st;  // column 4 - status: ESCAPED -> 0, EXITING -> 1, FOLLOWER -> 2, VISCEK -> 3
+            r[0] = __fmul2_rn(__fadd2_rn(q[k].p, nap), splat(inv_hyp));
+            r[1] = make_float2(st == ST_ESCAPED ? 1.f : 0.f, st == ST_EXITING ? 1.f : 0.f);
+            r[2] = make_float2(st == ST_FOLLOWER ? 1.f : 0.f, st == ST_VISCEK ? 1.f : 0.f);
+          }
+        }
+      } else if (MODE == WMODE_GRAV || a.positions == POS_GRAV) {
+        float gx = 0.f, gy = 0.f;
+        int nf = 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (q[k].st == ST_VISCEK) { float tx, ty; grav_term<float>(q[k].p.x, q[k].p.y, ap.x, ap.y, a, tx, ty); gx += tx; gy += ty; }
+          nf += (q[k].st == ST_FOLLOWER);
+        }
+        nf = __reduce_add_sync(0xffffffffu, nf);
+        const double wx = warp_sum((double)gx), wy = warp_sum((double)gy);
+        if (lane == 0) store_grav_obs<float>(row, ap.x, ap.y, (float)wx, (float)wy, nf, a);
+      } else {
+        if (lane == 0) store_head_obs<float>(row, ap.x, ap.y, a);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (valid[k]) store_ped_obs<float>(row, lane + 32 * k, N, q[k].p.x, q[k].p.y, q[k].st, ap.x, ap.y, a);
+      }
+    }
+    __syncwarp();  // the tile is rewritten by the next step
+  }  // steps
+
+  // ---------------- write back  // @region wwriteback
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (valid[k]) {
+      pos_e[lane + 32 * k] = q[k].p;
+      dir_e[lane + 32 * k] = q[k].d;
+      st_e[lane + 32 * k] = (uint8_t)q[k].st;
+    }
+  }
+  if (lane == 0) {
+    a.agent_pos[e] = ap; a.agent_dir[e] = ad;
+    a.now[e] = now; a.episode[e] = episode; a.overall[e] = overall;
+    a.acc[3 * (size_t)e] = acc_r; a.acc[3 * (size_t)e + 1] = acc_i; a.acc[3 * (size_t)e + 2] = acc_s;
+    if (a.reward) a.reward[e] = reward_sum;
+    if (a.terminated) a.terminated[e] = (uint8_t)any_term;
+    if (a.truncated) a.truncated[e] = (uint8_t)any_trunc;
+  }
+}
+
+}  // namespace evac

@@ -39,12 +39,45 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 }
 
 // Stream layout used everywhere in this library:
-//   counter = (index, step-in-episode `now`, episode index, global env index) with index =
-//             pedestrian (reset layout), pedestrian/4 (noise: one block serves 4 pedestrians), 0 (agent action)
-//   key     = (seed_lo ^ stream * 0x9E3779B9, seed_hi)
+//   4x32 (reset layout): counter = (pedestrian, 0, episode index, global env index),
+//                        key = (seed_lo ^ stream * 0x9E3779B9, seed_hi)
+//   2x32 (noise, agent): see evac_noise_block / evac_agent_block below
 __host__ __device__ __forceinline__ Philox4 evac_random(uint64_t seed, uint32_t stream, uint32_t env, uint32_t episode,
                                                         uint32_t now, uint32_t ped) {
   return philox4x32_10(ped, now, episode, env, (uint32_t)seed ^ (stream * 0x9E3779B9u), (uint32_t)(seed >> 32));
+}
+
+// Philox2x32-10: one 32x32 multiply per round -- the per-step angular noise (one block per lane = the lane's two
+// pedestrians) and the RandomAgent action use it; the (rare) reset layout keeps the 4x32 generator above.
+__host__ __device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p = (uint64_t)0xD256D193u * c0;
+    const uint32_t hi = (uint32_t)(p >> 32), lo = (uint32_t)p;
+    c0 = hi ^ k ^ c1;
+    c1 = lo;
+    k += 0x9E3779B9u;
+  }
+  return make_uint2(c0, c1);
+}
+
+// 32-bit key of the 2x32 streams: for a fixed seed it is a bijection of the episode index (odd multiplier), so
+// (env, episode, step, block) -> (counter, key) never collides within one run.
+__host__ __device__ __forceinline__ uint32_t evac_key32(uint64_t seed, uint32_t stream, uint32_t episode) {
+  return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ (episode * 0xBB67AE85u) ^ (stream * 0x85EBCA6Bu);
+}
+
+// Angular noise [area.py:124]: pedestrian i reads word (i >> 5) & 1 of block (i & 31) | (i >> 6) << 5 (block < 2048 for
+// N <= 4096), i.e. pedestrians i and i + 32 of every group of 64 share a block; counter = (block | now << 11, global env).
+__host__ __device__ __forceinline__ uint2 evac_noise_block(uint64_t seed, uint32_t env, uint32_t episode, uint32_t now, uint32_t block) {
+  return philox2x32_10(block | (now << 11), env, evac_key32(seed, STREAM_NOISE, episode));
+}
+__host__ __device__ __forceinline__ uint32_t evac_noise_block_of(uint32_t i) { return (i & 31u) | ((i >> 6) << 5); }
+__host__ __device__ __forceinline__ uint32_t evac_noise_word_of(uint32_t i) { return (i >> 5) & 1u; }
+
+// RandomAgent action (action_space.sample(), random_agent.py:8-9): words (x, y) of one block per (env, episode, step).
+__host__ __device__ __forceinline__ uint2 evac_agent_block(uint64_t seed, uint32_t env, uint32_t episode, uint32_t now) {
+  return philox2x32_10(now << 11, env, evac_key32(seed, STREAM_AGENT, episode));
 }
 
 // 24-bit uniform in [0,1): exactly representable in float32, so NumPy reproduces it bit for bit.

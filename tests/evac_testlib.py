@@ -81,17 +81,38 @@ def u01(r):
     return (np.asarray(r, dtype=np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
 
 
+_M2 = 0xD256D193
+
+
+def philox2x32_10(c0, c1, k):
+    """Vectorised Philox2x32-10 (csrc/philox.cuh::philox2x32_10); returns 2 uint32 arrays."""
+    c0, c1, k = (np.asarray(x, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for x in np.broadcast_arrays(c0, c1, k))
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p = np.uint64(_M2) * c0
+        hi, lo = p >> np.uint64(32), p & mask
+        c0, c1 = hi ^ k ^ c1, lo
+        k = (k + np.uint64(_W0)) & mask
+    return c0.astype(np.uint32), c1.astype(np.uint32)
+
+
+def evac_key32(seed, stream, episode):
+    return ((seed & 0xFFFFFFFF) ^ ((((seed >> 32) & 0xFFFFFFFF) * _W0) & 0xFFFFFFFF) ^ ((episode * _W1) & 0xFFFFFFFF)
+            ^ ((stream * 0x85EBCA6B) & 0xFFFFFFFF))
+
+
 def philox_noise(seed, env, episode, now, n, noise_coef):
-    """Dense [n] float32 noise the kernel draws for (env, episode, step-in-episode `now`): one Philox block
-    serves four pedestrians (pedestrian i = word i&3 of block i>>2)."""
-    nb = (n + 3) // 4
-    r = evac_random(seed, STREAM_NOISE, env, episode, now, np.arange(nb))
-    words = np.stack(r, axis=1).reshape(-1)[:n]
+    """Dense [n] float32 noise the kernels draw for (env, episode, step-in-episode `now`): pedestrian i reads word
+    (i >> 5) & 1 of Philox2x32 block (i & 31) | (i >> 6) << 5, counter (block | now << 11, env)."""
+    i = np.arange(n, dtype=np.int64)
+    block = (i & 31) | ((i >> 6) << 5)
+    r = philox2x32_10(block | (now << 11), env, evac_key32(seed, STREAM_NOISE, episode))
+    words = np.where(((i >> 5) & 1) == 1, r[1], r[0])
     return (u01(words) - np.float32(0.5)) * np.float32(noise_coef)
 
 
 def philox_action(seed, env, episode, now):
-    r = evac_random(seed, STREAM_AGENT, env, episode, now, 0)
+    r = philox2x32_10(now << 11, env, evac_key32(seed, STREAM_AGENT, episode))
     return np.array([np.float32(2) * u01(r[0]) - np.float32(1), np.float32(2) * u01(r[1]) - np.float32(1)], dtype=np.float32).reshape(2)
 
 

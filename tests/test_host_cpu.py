@@ -97,13 +97,17 @@ def test_spaces_and_agents():
 
 
 def test_philox_known_answers():
-    """Random123 known-answer vectors for Philox4x32-10."""
+    """Random123 known-answer vectors for Philox4x32-10 and Philox2x32-10."""
     kat = [((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
            ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
            ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
     for ctr, key, want in kat:
         got = T.philox4x32_10(*ctr, *key)
         assert tuple(int(x) for x in got) == want
+    for ctr, key, want in [((0, 0), 0, (0xFF1DAE59, 0x6CD10DF2)), ((0xFFFFFFFF, 0xFFFFFFFF), 0xFFFFFFFF, (0x2C3F628B, 0xAB4FD7AD)),
+                           ((0x243F6A88, 0x85A308D3), 0x13198A2E, (0xDD7CE038, 0xF62A4C12))]:  # Random123 kat_vectors, philox2x32 10
+        got = T.philox2x32_10(*ctr, key)
+        assert (int(got[0]), int(got[1])) == want
     nz = T.philox_noise(7, 3, 1, 0, 60, 0.2)
     assert nz.dtype == np.float32 and np.all(np.abs(nz) <= 0.1) and len(np.unique(nz)) > 50
 

@@ -1,14 +1,11 @@
-"""Executed warp-instructions of the step kernel grouped by code region (source-line ranges of
-evac_kernels.cuh), from `ncu -i X.ncu-rep --page source --csv --print-source cuda,sass`.
-Usage: ... | python tools/ncu_regions.py <warps-launched> """
+"""List the SASS of one region (see tools/ncu_regions.py) with executed counts per warp.
+Usage: ncu -i X.ncu-rep --page source --csv --print-source cuda,sass | python tools/ncu_region_sass.py <region> <warps>"""
 import csv
 import re
 import sys
-from collections import defaultdict
 
 rows = list(csv.reader(sys.stdin))
-warps = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-# region markers: a line `// @region name` in a .cuh starts a region (until the next marker)
+region, warps = sys.argv[1], float(sys.argv[2])
 OWN = ("evac_kernels.cuh", "evac_warp.cuh")
 marks = {f: [(i + 1, m.group(1)) for i, l in enumerate(open("evacuation_b200/csrc/" + f).read().splitlines())
              for m in [re.search(r"@region\s+(\S+)", l)] if m] for f in OWN}
@@ -28,10 +25,8 @@ def region_of(fname, line):
     return name
 
 
-# every SASS address is listed once per level of its inline stack (callee line, call-site line, ...):
-# attribute it ONCE, to the region of its call site inside the kernel body (the deepest evac_kernels.cuh line).
-addr = {}
-KERNEL_FILE = next((r[1].split("/")[-1] for r in rows if r and r[0] == "File Path"), "")  # the kernel body's file comes first
+KERNEL_FILE = next((r[1].split("/")[-1] for r in rows if r and r[0] == "File Path"), "")
+addr, order = {}, []
 cur_file, cur_line, hdr, first_fn, skip = "", None, None, None, False
 for r in rows:
     if not r:
@@ -55,13 +50,11 @@ for r in rows:
     elif cur_line is not None and r[2].startswith("0x"):
         key = ((2 if cur_file == KERNEL_FILE else 1), cur_line) if cur_file in OWN else (0, 0)
         prev = addr.get(r[2])
+        if prev is None:
+            order.append(r[2])
         if prev is None or key > prev[0]:
-            addr[r[2]] = (key, region_of(cur_file, cur_line), int(r[ix] or 0), int(r[isamp] or 0))
-inst, samp = defaultdict(int), defaultdict(int)
-for _, reg, n, sm in addr.values():
-    inst[reg] += n
-    samp[reg] += sm
-tot, ts = sum(inst.values()), sum(samp.values())
-print(f"kernel: {first_fn[:80]}\ntotal warp-inst {tot}  ({tot / warps:.0f} per warp)  samples {ts}")
-for k, v in sorted(inst.items(), key=lambda kv: -kv[1]):
-    print(f"{k:14s} {v:10d} {100 * v / tot:5.1f}%  {v / warps:7.1f}/warp   stall-samples {100 * samp[k] / max(ts, 1):5.1f}%")
+            addr[r[2]] = (key, region_of(cur_file, cur_line), int(r[ix] or 0), int(r[isamp] or 0), r[3], cur_file, cur_line)
+for ad in sorted(addr):
+    key, reg, n, sm, sass, f, ln = addr[ad]
+    if reg == region and n:
+        print(f"{ad[-5:]} {n / warps:6.2f} s{sm:3d} {f[:12]}:{ln:<4d} {sass.strip()}")

@@ -1,6 +1,6 @@
 """evacuation_b200 -- B200-native batched implementation of the cinemere/evacuation
 environment step, behind the reference's own Python API (src/env/__init__.py:3-21)."""
-from .agents import BaseAgent, RandomAgent, RotatingAgent
+from .agents import BaseAgent, RandomAgent, RotatingAgent, WacuumCleaner
 from .config import EnvConfig, EnvWrappersConfig
 from .env import EvacuationEnv
 from .statuses import Status, SwitchDistances
@@ -9,7 +9,7 @@ from .wrappers import GravityEncoding, MatrixObs, PedestriansStatuses, RelativeP
 __all__ = [
     "setup_env", "EvacuationEnv", "Status", "SwitchDistances", "EnvConfig", "EnvWrappersConfig",
     "GravityEncoding", "PedestriansStatuses", "RelativePosition", "MatrixObs",
-    "BaseAgent", "RandomAgent", "RotatingAgent",
+    "BaseAgent", "RandomAgent", "RotatingAgent", "WacuumCleaner",
 ]
 
 

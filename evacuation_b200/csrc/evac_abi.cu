@@ -283,9 +283,9 @@ int evac_destroy(EvacHandle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   void* dptrs[] = {h->pos, h->dir, h->status, h->agent_pos, h->agent_dir, h->now, h->episode, h->overall, h->acc,
-                   h->ep_stats, h->ep_finished, h->totals, h->d_actions, h->d_noise, h->d_obs, h->d_reward, h->d_term, h->d_trunc};
+                   h->ep_stats, h->ep_finished, h->totals, h->d_actions, h->d_noise, h->d_obs /* one block: obs | reward | flags */};
   for (void* p : dptrs) if (p) cudaFree(p);
-  void* hptrs[] = {h->h_actions, h->h_noise, h->h_obs, h->h_reward, h->h_term, h->h_trunc};
+  void* hptrs[] = {h->h_actions, h->h_noise, h->h_obs /* one block */};
   for (void* p : hptrs) if (p) cudaFreeHost(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -387,10 +387,13 @@ int evac_step_host(EvacHandle* h, const float* actions, const float* noise, floa
   const size_t E = h->E, N = h->N, D = h->obs_dim;
   if (!h->h_actions) {
     CK(cudaMallocHost((void**)&h->h_actions, E * 8)); CK(cudaMalloc((void**)&h->d_actions, E * 8));
-    CK(cudaMallocHost((void**)&h->h_obs, E * D * 4)); CK(cudaMalloc((void**)&h->d_obs, E * D * 4));
-    CK(cudaMallocHost((void**)&h->h_reward, E * 4)); CK(cudaMalloc((void**)&h->d_reward, E * 4));
-    CK(cudaMallocHost((void**)&h->h_term, E)); CK(cudaMalloc((void**)&h->d_term, E));
-    CK(cudaMallocHost((void**)&h->h_trunc, E)); CK(cudaMalloc((void**)&h->d_trunc, E));
+    // outputs live in ONE device block and ONE pinned block, [obs | reward | terminated | truncated], so a caller
+    // whose (page-locked) result arrays are laid out the same way gets them with a single D2H copy
+    const size_t out_bytes = E * D * 4 + E * 4 + 2 * E;
+    unsigned char *hb = nullptr, *db = nullptr;
+    CK(cudaMallocHost((void**)&hb, out_bytes)); CK(cudaMalloc((void**)&db, out_bytes));
+    h->h_obs = (float*)hb; h->h_reward = (float*)(hb + E * D * 4); h->h_term = hb + E * D * 4 + E * 4; h->h_trunc = h->h_term + E;
+    h->d_obs = (float*)db; h->d_reward = (float*)(db + E * D * 4); h->d_term = db + E * D * 4 + E * 4; h->d_trunc = h->d_term + E;
   }
   if (noise && !h->h_noise) { CK(cudaMallocHost((void**)&h->h_noise, E * N * 4)); CK(cudaMalloc((void**)&h->d_noise, E * N * 4)); }
   cudaStream_t st = h->stream;
@@ -405,10 +408,16 @@ int evac_step_host(EvacHandle* h, const float* actions, const float* noise, floa
     CK(cudaMemcpyAsync(h->d_noise, pn ? noise : h->h_noise, E * N * 4, cudaMemcpyHostToDevice, st));
   }
   if (int r = evac_step(h, h->d_actions, noise ? h->d_noise : nullptr, obs ? h->d_obs : nullptr, h->d_reward, h->d_term, h->d_trunc, st)) return r;
-  if (obs) CK(cudaMemcpyAsync(po ? obs : h->h_obs, h->d_obs, E * D * 4, cudaMemcpyDeviceToHost, st));
-  if (reward) CK(cudaMemcpyAsync(pr ? reward : h->h_reward, h->d_reward, E * 4, cudaMemcpyDeviceToHost, st));
-  if (terminated) CK(cudaMemcpyAsync(pt ? terminated : h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, st));
-  if (truncated) CK(cudaMemcpyAsync(pu ? truncated : h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, st));
+  const bool packed_pinned = po && pr && pt && pu && reward == obs + E * D && terminated == (uint8_t*)(reward + E) && truncated == terminated + E;
+  const bool all_pageable = !po && !pr && !pt && !pu && obs && reward && terminated && truncated;
+  if (packed_pinned || all_pageable) {
+    CK(cudaMemcpyAsync(packed_pinned ? (void*)obs : (void*)h->h_obs, h->d_obs, E * D * 4 + E * 4 + 2 * E, cudaMemcpyDeviceToHost, st));
+  } else {
+    if (obs) CK(cudaMemcpyAsync(po ? obs : h->h_obs, h->d_obs, E * D * 4, cudaMemcpyDeviceToHost, st));
+    if (reward) CK(cudaMemcpyAsync(pr ? reward : h->h_reward, h->d_reward, E * 4, cudaMemcpyDeviceToHost, st));
+    if (terminated) CK(cudaMemcpyAsync(pt ? terminated : h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, st));
+    if (truncated) CK(cudaMemcpyAsync(pu ? truncated : h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, st));
+  }
   CK(cudaStreamSynchronize(st));
   if (obs && !po) memcpy(obs, h->h_obs, E * D * 4);
   if (reward && !pr) memcpy(reward, h->h_reward, E * 4);

@@ -215,9 +215,9 @@ class EvacuationEnv:
         nat.check(lib.evac_create(C.byref(c), self.num_envs, self.device.index, C.c_uint64(self.seed_value),
                                   C.c_int64(self.env_index_offset), C.byref(h)))
         self._h = h
-        self.obs_dim = lib.evac_obs_dim(h)
+        self._obs_dim = lib.evac_obs_dim(h)
         E, dev = self.num_envs, self.device
-        self._obs = torch.empty((E, self.obs_dim), dtype=torch.float32, device=dev)
+        self._obs = torch.empty((E, self._obs_dim), dtype=torch.float32, device=dev)
         self._reward = torch.empty(E, dtype=torch.float32, device=dev)
         self._terminated = torch.empty(E, dtype=torch.uint8, device=dev)
         self._truncated = torch.empty(E, dtype=torch.uint8, device=dev)
@@ -239,6 +239,12 @@ class EvacuationEnv:
             self.close()
         except Exception:
             pass
+
+    @property
+    def obs_dim(self) -> int:
+        """Floats per environment in one flat observation row."""
+        self._handle()
+        return self._obs_dim
 
     @property
     def num_cells(self) -> int:
@@ -379,9 +385,12 @@ class EvacuationEnv:
             noise = self._numpy_noise()
         nz = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float32).reshape(E, N))
         if self._host is None:
-            pin = dict(pin_memory=True)
-            self._host = dict(obs=torch.empty((E, self.obs_dim), dtype=torch.float32, **pin), rew=torch.empty(E, dtype=torch.float32, **pin),
-                              term=torch.empty(E, dtype=torch.uint8, **pin), trunc=torch.empty(E, dtype=torch.uint8, **pin))
+            # ONE page-locked block [obs | reward | terminated | truncated]: evac_step_host fills it with a single D2H copy
+            D = self.obs_dim
+            blk = torch.empty(E * D * 4 + E * 4 + 2 * E, dtype=torch.uint8, pin_memory=True)
+            o0, r0, t0 = E * D * 4, E * D * 4 + E * 4, E * D * 4 + E * 4 + E
+            self._host_block = blk
+            self._host = dict(obs=blk[:o0].view(torch.float32).view(E, D), rew=blk[o0:r0].view(torch.float32), term=blk[r0:t0], trunc=blk[t0:])
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
         hb = self._host
         # outputs alias the page-locked buffers and are valid until the next step (the reference's

@@ -1,0 +1,106 @@
+"""CPU tests of the rollout-loop glue (evacuation_b200/rollout.py): the policy restatement against a golden
+produced by the unmodified reference network, and the per-env running normalisers against a NumPy restatement of
+gymnasium's RunningMeanStd."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from evacuation_b200.rollout import RPOTransformerPolicy, VectorNormalizer
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load_policy():
+    z = np.load(os.path.join(HERE, "golden", "policy", "policy_transformer.npz"))
+    n = int(z["number_of_pedestrians"])
+    x = torch.as_tensor(z["x"])
+    net = RPOTransformerPolicy(x.shape[1], n).eval()
+    sd = {k[2:]: torch.as_tensor(z[k]) for k in z.files if k.startswith("w:")}
+    missing, unexpected = net.load_state_dict(sd, strict=True)  # same parameter names / shapes as the reference module
+    assert not missing and not unexpected
+    return z, x, net
+
+
+def test_policy_matches_reference_network_golden():
+    z, x, net = _load_policy()
+    with torch.no_grad():
+        emb = net.embed(x)
+        np.testing.assert_allclose(emb.numpy(), z["embedding"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(net.actor_mean(emb).numpy(), z["actor_mean"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(net.get_value(x).numpy(), z["value"], rtol=1e-5, atol=1e-6)
+        # log-probability / entropy of the action the reference sampled
+        a = torch.as_tensor(z["sampled_action"])
+        mean = net.actor_mean(emb)
+        std = torch.exp(net.actor_logstd.expand_as(mean))
+        lp = torch.distributions.Normal(mean, std).log_prob(a).sum(1)
+        np.testing.assert_allclose(lp.numpy(), z["logprob_of_sampled"], rtol=1e-5, atol=1e-6)
+        _, lp2, ent, v = net.get_action_and_value(x)
+        np.testing.assert_allclose(ent.numpy(), z["entropy"], rtol=1e-6)
+        np.testing.assert_allclose(v.numpy(), z["value"], rtol=1e-5, atol=1e-6)
+
+
+def test_policy_chunking_is_transparent():
+    z, x, net = _load_policy()
+    net.chunk = 2
+    with torch.no_grad():
+        np.testing.assert_allclose(net.embed(x).numpy(), z["embedding"], rtol=1e-5, atol=1e-6)
+
+
+class _RMS:  # gymnasium.wrappers.normalize.RunningMeanStd restated (float64)
+    def __init__(self, shape):
+        self.mean, self.var, self.count = np.zeros(shape), np.ones(shape), 1e-4
+
+    def update(self, x):
+        bm, bv, bc = x.mean(axis=0), x.var(axis=0), x.shape[0]
+        delta = bm - self.mean
+        tot = self.count + bc
+        self.mean = self.mean + delta * bc / tot
+        m2 = self.var * self.count + bv * bc + delta ** 2 * self.count * bc / tot
+        self.var, self.count = m2 / tot, tot
+
+
+def test_vector_normalizer_matches_gymnasium_running_mean_std():
+    E, D, T, gamma = 3, 5, 40, 0.99
+    rs = np.random.RandomState(0)
+    norm = VectorNormalizer(E, D, gamma=gamma, device="cpu", dtype=torch.float64)
+    obs_rms = [_RMS((D,)) for _ in range(E)]
+    ret_rms = [_RMS(()) for _ in range(E)]
+    returns = np.zeros(E)
+    for t in range(T):
+        obs = rs.normal(0.3, 2.0, (E, D))
+        rew = rs.normal(-1, 3, E)
+        term = rs.rand(E) < 0.1
+        got_o = norm.observation(torch.as_tensor(obs)).numpy()
+        got_r = norm.reward(torch.as_tensor(rew), torch.as_tensor(term)).numpy()
+        for e in range(E):
+            obs_rms[e].update(obs[e][None])
+            want_o = np.clip((obs[e] - obs_rms[e].mean) / np.sqrt(obs_rms[e].var + 1e-8), -1, 1)
+            np.testing.assert_allclose(got_o[e], want_o, rtol=1e-9, atol=1e-12)
+            returns[e] = returns[e] * gamma * (1 - term[e]) + rew[e]
+            ret_rms[e].update(np.array([returns[e]]))
+            want_r = np.clip(rew[e] / np.sqrt(ret_rms[e].var + 1e-8), -100, 100)
+            np.testing.assert_allclose(got_r[e], want_r, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["unit", "wide"])
+def test_wacuum_cleaner_matches_reference_trace(tag):
+    """The sweep baseline (single-env NumPy face and the batched torch state machine) against the action trace of the
+    unmodified reference class (tests/golden/policy/gen_wacuum_golden.py)."""
+    from types import SimpleNamespace as NS
+
+    from evacuation_b200.agents import WacuumCleaner
+
+    z = np.load(os.path.join(HERE, "golden", "policy", "wacuum_actions.npz"))
+    w, h, step = z[tag + "_cfg"]
+    area = NS(width=w, height=h, step_size=step, exit=NS(position=np.array([0, -1], dtype=np.float32)))
+    env = NS(area=area, num_envs=2, device="cpu")
+    env.unwrapped = env
+    single, batched = WacuumCleaner(env), WacuumCleaner.batched(env)
+    for pos, want in zip(z[tag + "_pos"], z[tag + "_act"]):
+        got = single.act({"agent_position": pos})
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-7)
+        gb = batched.act(torch.as_tensor(np.stack([pos, pos]))).numpy()
+        np.testing.assert_allclose(gb[0], want, rtol=0, atol=1e-7)
+        np.testing.assert_allclose(gb[1], want, rtol=0, atol=1e-7)

@@ -339,11 +339,64 @@ def run_ours(args):
             "clocks": clocks,
             "episodes_finished_all_ranks": float(totals[:, 0].sum()),
         }
+        if world == 1 and not args.no_extra:
+            line["other_workloads"] = other_workloads(dev)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single_core(args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_workloads(dev):
+    """Secondary BASELINE.json configs (parity-test cases, not the bench line): a short device-timed measurement of
+    each so that one bench run documents them.  K steps inside one rollout launch (on-device RandomAgent, same-step
+    auto-reset) after 64 warm-up steps; config 5 additionally with the RPO transformer-embedding policy in the loop."""
+    import torch
+
+    import evacuation_b200 as eb
+
+    def rollout_us(env_kw, wrap_kw, E, K, **kw):
+        env = eb.setup_env(eb.EnvConfig(**env_kw), eb.EnvWrappersConfig(**wrap_kw), num_envs=E, device=dev, seed=7, auto_reset=True, **kw)
+        env.reset()
+        env.rollout(64, agent="random")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        env.rollout(K, agent="random")
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = 1e3 * e0.elapsed_time(e1) / K
+        n = env_kw["number_of_pedestrians"]
+        env.unwrapped.close()
+        return {"envs": E, "pedestrians": n, "us_per_step": us, "pedestrian_steps_per_s": E * n / us * 1e6, "env_steps_per_s": E / us * 1e6,
+                "fp32_frac_algorithmic": E * algorithmic_flops_per_env_step(n) / (us * 1e-6) / (148 * 128 * 2 * 1.965e9)}
+
+    out = {}
+    out["c3_grav_4096x60"] = rollout_us(dict(number_of_pedestrians=60, enslaving_degree=0.5, noise_coef=0.5), dict(positions="grav", alpha=3), 4096, 200)
+    out["c4_large_crowd_256x4096_cells"] = rollout_us(dict(number_of_pedestrians=4096), WRAP_KW, 256, 20)
+    out["c4_large_crowd_256x4096_all_pairs"] = rollout_us(dict(number_of_pedestrians=4096), WRAP_KW, 256, 4, neighbor_search="brute")
+    out["c5_env_only_65536x60"] = rollout_us(ENV_KW, WRAP_KW, 65536, 100)
+    # config 5, one rank's share of the 8-GPU job (65536 / 8 envs) with the policy in the loop
+    from evacuation_b200.rollout import PolicyRollout, RPOTransformerPolicy
+
+    E = 8192
+    env = eb.setup_env(eb.EnvConfig(**ENV_KW), eb.EnvWrappersConfig(**WRAP_KW), num_envs=E, device=dev, seed=7, auto_reset=True)
+    torch.manual_seed(1)
+    ro = PolicyRollout(env, RPOTransformerPolicy(env.unwrapped.obs_dim, N_PED).to(dev), use_graph=True, store=False)
+    ro.reset()
+    ro.run(4)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    ro.run(8)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 8
+    out["c5_policy_loop_8192x60"] = {"envs": E, "pedestrians": N_PED, "ms_per_step": ms, "pedestrian_steps_per_s": E * N_PED / ms * 1e3,
+                                     "note": "RPO transformer-embedding policy forward (PyTorch, random init) -> ClipAction -> fused env step -> "
+                                             "Normalize{Observation,Reward}, CUDA-graph replayed; the policy is >99 % of the loop"}
+    return out
 
 
 def main():
@@ -355,6 +408,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_workloads leg (secondary BASELINE configs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -65,6 +65,7 @@ SIGNATURES = {
     "evac_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "evac_rollout": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "evac_episode_stats": (C.c_int, [_P, _P, _P, _P, _P]),
+    "evac_get_accumulators": (C.c_int, [_P, _P, _P, _P]),
     "evac_launch_count": (C.c_int64, [_P]),
     "evac_probe_fma": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "evac_probe_pairwise": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double)]),

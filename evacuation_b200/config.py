@@ -28,7 +28,7 @@ class EnvConfig:
     max_timesteps: int = 2_000
     n_episodes: int = 0
     n_timesteps: int = 0
-    # ---- logging / drawing (accepted for drop-in compatibility; rendering is out of scope)
+    # ---- logging / drawing (env.py:23-31,110-127,153-165): host-side, for the tracked environment (env.unwrapped.tracked_env)
     render_mode: Optional[str] = None
     draw: bool = False
     verbose: bool = False

@@ -257,6 +257,13 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
     const double edge = cfg->to_pedestrian * (1.0 + 1e-4);
     const int gx = (int)fmin(64.0, floor(2.0 * cfg->width / edge)), gy = (int)fmin(64.0, floor(2.0 * cfg->height / edge));
     if (gx >= 1 && gy >= 1 && (cfg->neighbor_search == EVAC_SEARCH_CELLS || gx * gy >= 16)) { h->cells_x = gx; h->cells_y = gy; }
+  } else if (h->threads == 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search == EVAC_SEARCH_CELLS) {
+    // one-warp kernel, opt-in: vertical strips (a 1-D cell list, at most 32 strips), same edge rule.  Measured on
+    // B200 (profiles/README.md): 15 % fewer instructions than the all-pairs tile but no wall-clock gain (the warp is
+    // latency-bound and the per-lane windows turn the broadcast LDS.128 into conflicting ones), and the all-pairs
+    // tile sums in pedestrian-index order like the reference -> AUTO keeps all pairs for N <= 64.
+    const int gx = (int)fmin(32.0, floor(2.0 * cfg->width / (cfg->to_pedestrian * (1.0 + 1e-4))));
+    if (gx >= 1) { h->cells_x = gx; h->cells_y = 1; }
   }
   const size_t en = (size_t)h->E * h->N, es = h->prec == EVAC_PREC_F64 ? 16 : 8;
 #define ALLOC(ptr, bytes)                                                      \
@@ -423,6 +430,15 @@ int evac_step_host(EvacHandle* h, const float* actions, const float* noise, floa
   if (reward && !pr) memcpy(reward, h->h_reward, E * 4);
   if (terminated && !pt) memcpy(terminated, h->h_term, E);
   if (truncated && !pu) memcpy(truncated, h->h_trunc, E);
+  return EVAC_OK;
+}
+
+int evac_get_accumulators(EvacHandle* h, double* acc, int64_t* overall_timesteps, void* stream) {
+  if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
+  if (int r = set_device(h)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (acc) CK(cudaMemcpyAsync(acc, h->acc, (size_t)h->E * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (overall_timesteps) CK(cudaMemcpyAsync(overall_timesteps, h->overall, (size_t)h->E * sizeof(long long), cudaMemcpyDeviceToDevice, st));
   return EVAC_OK;
 }
 

@@ -17,6 +17,31 @@ enum { WMODE_GENERIC = 0, WMODE_REL_OHE_BOX = 1, WMODE_GRAV = 2 };
 
 __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 
+// Neighbour sums of ONE pedestrian over the slot pairs [j0, j1) of the strip-sorted tile (same packed evaluation as
+// pairwise_pass; trip counts differ per lane, finished lanes idle).
+__device__ __forceinline__ void windowed_pass(const Tile<float>& t, int j0, int j1, float x, float y, float thr2, float& sx, float& sy) {
+  const float2 nx = splat(-x), ny = splat(-y);
+  float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
+  if (j0 < j1) {
+    float4 p = t.P2[j0], u = t.U2[j0];
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+      const float4 pn = t.P2[j + 1], un = t.U2[j + 1];  // look-ahead (at most the tile's spare entry)
+      const float2 dx = __fadd2_rn(make_float2(p.x, p.y), nx);
+      const float2 dy = __fadd2_rn(make_float2(p.z, p.w), ny);
+      float2 d2 = __fmul2_rn(dx, dx);
+      d2 = __ffma2_rn(dy, dy, d2);
+      const float2 w = make_float2(d2.x < thr2 ? 1.f : 0.f, d2.y < thr2 ? 1.f : 0.f);
+      ax = __ffma2_rn(w, make_float2(u.x, u.y), ax);
+      ay = __ffma2_rn(w, make_float2(u.z, u.w), ay);
+      p = pn;
+      u = un;
+    }
+  }
+  sx = ax.x + ax.y;
+  sy = ay.x + ay.y;
+}
+
 // per-pedestrian working set of the warp kernel
 struct WPed {
   float2 p, d;  // position, direction
@@ -27,6 +52,11 @@ template <int MODE>
 __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
   __shared__ __align__(16) float4 tile_s[66];  // Tile<float> of 64 slots (+ the look-ahead entries)
   const Tile<float> tile(reinterpret_cast<unsigned char*>(tile_s), 64);
+  // strip culling (a.cells_x > 0): the sources are sorted by vertical strip (edge >= vision radius) so that a
+  // pedestrian only visits the slots of its own and the two adjacent strips
+  __shared__ uint2 strip_mask[32];   // per strip: which lanes' pedestrian 0 (.x) / pedestrian 1 (.y) sit in it
+  __shared__ int strip_start[33];    // first slot of every strip (+ total)
+  const int S = a.cells_x;
   const int lane = threadIdx.x, e = blockIdx.x, N = a.N;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const bool valid[2] = {lane < N, lane + 32 < N};
@@ -69,6 +99,9 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
     const int now_prev = now;
     now += 1;
     const bool truncated = now >= a.max_timesteps;
+    // the action is requested first so that its (cold) latency overlaps the preparation below
+    float2 act_tbl = make_float2(0.f, 0.f);
+    if (a.agent_kind == AGENT_TABLE) act_tbl = a.actions[(size_t)s * a.E + e];
     // ---------------- angular noise of this lane's two pedestrians [area.py:124]
     float nz[2];
     if (noise_e != nullptr) {
@@ -100,14 +133,55 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
     }
     // ---------------- compact the moving pedestrians into the shared tile  // @region wcompact
     int n_src;
-    {
+    int win_lo[2] = {0, 0}, win_hi[2] = {0, 0};  // slot window of this lane's pedestrians (strip culling)
+    bool culled = false;
+    if (S > 0) {
+      // deterministic counting sort by strip: atomicOr of lane bits (commutative, so the result does not depend on
+      // the order the atomics retire), rank = number of lower (pedestrian, lane) pairs of the same strip
+      int c[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) c[k] = min(max((int)((q[k].p.x + a.width_f) * a.cell_inv_x), 0), S - 1);  // (int)NaN == 0
+      strip_mask[lane] = make_uint2(0u, 0u);
+      __syncwarp();
+      if (efv[0]) atomicOr(&strip_mask[c[0]].x, 1u << lane);
+      if (efv[1]) atomicOr(&strip_mask[c[1]].y, 1u << lane);
+      __syncwarp();
+      {
+        const uint2 m = strip_mask[lane];
+        const int cnt = (lane < S) ? __popc(m.x) + __popc(m.y) : 0;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        strip_start[lane] = inc - cnt;
+        if (lane == 31) strip_start[32] = inc;
+        n_src = __shfl_sync(0xffffffffu, inc, 31);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (efv[k]) {
+          const uint2 m = strip_mask[c[k]];
+          const int slot = strip_start[c[k]] + (k == 0 ? __popc(m.x & lt_mask) : __popc(m.x) + __popc(m.y & lt_mask));
+          tile.put(slot, q[k].p.x, q[k].p.y, u[k].x, u[k].y);
+        }
+        if (fv[k]) {
+          win_lo[k] = strip_start[max(c[k] - 1, 0)] >> 1;                      // in slot PAIRS: a neighbouring slot that
+          win_hi[k] = (strip_start[min(c[k] + 1, S - 1) + 1] + 1) >> 1;        // rides along fails the distance test
+        }
+      }
+      // cost model: two windowed loops (one pedestrian each) against one all-pairs loop shared by both pedestrians;
+      // a source without a direction (NaN) poisons every sum in the reference -> all-pairs path reproduces that
+      const int wmax0 = __reduce_max_sync(0xffffffffu, win_hi[0] - win_lo[0]), wmax1 = __reduce_max_sync(0xffffffffu, win_hi[1] - win_lo[1]);
+      const bool nan_src = (efv[0] && (u[0].x != u[0].x || u[0].y != u[0].y)) || (efv[1] && (u[1].x != u[1].x || u[1].y != u[1].y));
+      culled = (wmax0 + wmax1) * 5 < ((n_src + 1) >> 1) * 8 && !__any_sync(0xffffffffu, nan_src);
+    } else {
       const uint32_t m0 = __ballot_sync(0xffffffffu, efv[0]), m1 = __ballot_sync(0xffffffffu, efv[1]);
       const int c0 = __popc(m0);
       if (efv[0]) tile.put(__popc(m0 & lt_mask), q[0].p.x, q[0].p.y, u[0].x, u[0].y);
       if (efv[1]) tile.put(c0 + __popc(m1 & lt_mask), q[1].p.x, q[1].p.y, u[1].x, u[1].y);
       n_src = c0 + __popc(m1);
-      if (lane < 2) tile.put(n_src + lane, PARK, PARK, 0.f, 0.f);  // pad to an even count
     }
+    if (lane < 2) tile.put(n_src + lane, PARK, PARK, 0.f, 0.f);  // pad to an even count
     __syncwarp();
     // ---------------- action source + Area.agent_step [area.py:182-210], IEEE float32 like the reference  // @region wagent
     float r_agent = 0.f;
@@ -115,8 +189,7 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
     {
       float ax, ay;
       if (a.agent_kind == AGENT_TABLE) {
-        const float2 av = a.actions[(size_t)s * a.E + e];
-        ax = av.x; ay = av.y;
+        ax = act_tbl.x; ay = act_tbl.y;
       } else if (a.agent_kind == AGENT_RANDOM) {  // RandomAgent: action_space.sample() ~ U[-1,1)^2 [random_agent.py:8-9]
         const uint2 r = evac_agent_block(a.seed, env_g, (uint32_t)episode, (uint32_t)now_prev);
         ax = 2.f * u01(r.x) - 1.f; ay = 2.f * u01(r.y) - 1.f;
@@ -134,7 +207,10 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
     }
     // ---------------- pairwise alignment [area.py:105-119]  // @region wpairwise
     float sx[2], sy[2], cnt[2];
-    {
+    if (culled) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) windowed_pass(tile, win_lo[k], win_hi[k], q[k].p.x, q[k].p.y, a.thr2_ped, sx[k], sy[k]);
+    } else {
       const float xi[2] = {q[0].p.x, q[1].p.x}, yi[2] = {q[0].p.y, q[1].p.y};
       if (__any_sync(0xffffffffu, fv[0] | fv[1])) pairwise_pass<2, false>(tile, n_src, xi, yi, a.thr2_ped, sx, sy, cnt);
       else sx[0] = sx[1] = sy[0] = sy[1] = 0.f;

@@ -20,6 +20,8 @@ a GPU raises.
 from __future__ import annotations
 
 import ctypes as C
+import logging
+import os
 from typing import Optional
 
 import numpy as np
@@ -29,6 +31,8 @@ from . import _native as nat
 from .config import EnvConfig
 from .spaces import Box, Dict
 from .statuses import Status, SwitchDistances
+
+log = logging.getLogger(__name__)
 
 _TORCH_STATE_DTYPE = {"fp32": torch.float32, "fp64": torch.float64}
 
@@ -43,6 +47,14 @@ class _Pedestrians:
     def __init__(self, env: "EvacuationEnv"):
         self._env = env
         self.num = env.cfg.number_of_pedestrians
+        self.memory = {"positions": [], "statuses": []}  # pedestrians.py:14 (trajectory of the tracked environment)
+
+    def save(self):
+        """pedestrians.py:33-35: append the tracked environment's positions / statuses (host copies)."""
+        st = self._env.get_state()
+        e = self._env.tracked_env
+        self.memory["positions"].append(st["positions"][e].cpu().numpy().astype(np.float64))
+        self.memory["statuses"].append(st["statuses"][e].cpu().numpy())
 
     def _fetch(self, key):
         v = self._env.get_state()[key]
@@ -79,6 +91,10 @@ class _Agent:
         self.enslaving_degree = env.cfg.enslaving_degree
         self.start_position = np.zeros(2, dtype=np.float32)
         self.start_direction = np.zeros(2, dtype=np.float32)
+        self.memory = {"position": []}  # area.py:24
+
+    def save(self):  # area.py:32-33
+        self.memory["position"].append(self._env.get_state()["agent_position"][self._env.tracked_env].cpu().numpy().copy())
 
     @property
     def position(self):
@@ -107,6 +123,12 @@ class _Time:
     def __init__(self, env: "EvacuationEnv"):
         self._env = env
         self.max_timesteps = env.cfg.max_timesteps
+        self.n_episodes = 0  # resets seen by this Python object (area.py:49-51)
+
+    @property
+    def overall_timesteps(self):
+        v = self._env.accumulators()[1]
+        return v if self._env.batched else int(v[0])
 
     @property
     def now(self):
@@ -167,6 +189,14 @@ class EvacuationEnv:
         })
         self.render_mode = cfg.render_mode
         self.experiment_name = cfg.experiment_name
+        # ---- logging / trajectory capture (env.py:23-31,45-64): host-side, off the per-step device path
+        self.draw = bool(cfg.draw)
+        self.giff_freq = cfg.giff_freq
+        self.save_next_episode_anim = False
+        self.wandb_enabled = bool(cfg.wandb_enabled)
+        self.path_giff, self.path_png = cfg.path_giff, cfg.path_png
+        self.tracked_env = 0  # index of the environment whose trajectory `draw` records
+        self._file_logging = False
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -293,6 +323,54 @@ class EvacuationEnv:
         nat.check(lib.evac_set_state(h, _ptr(p), _ptr(d), _ptr(s), _ptr(ap), _ptr(ad), _ptr(nw), self._stream()))
         self._host_statuses = None
 
+    def accumulators(self):
+        """(acc [E,3] float64: episode_reward, episode_intrinsic_reward, episode_status_reward; overall_timesteps [E] int64)
+        of the running episodes (env.py:65-67,168-170)."""
+        h, lib = self._handle(), nat.load()
+        acc = torch.empty((self.num_envs, 3), dtype=torch.float64, device=self.device)
+        overall = torch.empty(self.num_envs, dtype=torch.int64, device=self.device)
+        nat.check(lib.evac_get_accumulators(h, _ptr(acc), _ptr(overall), self._stream()))
+        return acc, overall
+
+    # ------------------------------------------------------------------ logging (env.py:23-31,114-127)
+    def _setup_logging(self):
+        if self._file_logging:
+            return
+        os.makedirs(self.cfg.path_logs, exist_ok=True)
+        handler = logging.FileHandler(os.path.join(self.cfg.path_logs, f"logs_{self.experiment_name}.log"), mode="w")
+        handler.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s"))
+        log.addHandler(handler)
+        log.setLevel(logging.DEBUG if self.cfg.verbose else logging.INFO)
+        self._file_logging = True
+
+    def episode_log(self, env_index: int = 0) -> dict:
+        """The per-episode logging dict of env.py:115-125 for the RUNNING episode of one environment."""
+        acc, overall = self.accumulators()
+        st = self.get_state()
+        s = st["statuses"][env_index]
+        return {
+            "episode_intrinsic_reward": float(acc[env_index, 1]), "episode_status_reward": float(acc[env_index, 2]),
+            "episode_reward": float(acc[env_index, 0]), "episode_length": int(st["now"][env_index]),
+            "escaped_pedestrians": int((s == 4).sum()), "exiting_pedestrians": int((s == 3).sum()),
+            "following_pedestrians": int((s == 2).sum()), "viscek_pedestrians": int((s == 1).sum()),
+            "overall_timesteps": int(overall[env_index]),
+        }
+
+    def _log_finished_episode(self):
+        """What the reference does at the top of reset() (env.py:114-127): log the episode that just ended."""
+        d = self.episode_log(self.tracked_env)
+        self._setup_logging()
+        log.info("\t".join(f"{k}={v}" for k, v in d.items()))
+        if self.wandb_enabled:
+            try:
+                import wandb
+
+                if wandb.run is not None:
+                    wandb.log(d)
+            except ImportError:
+                pass
+        return d
+
     # ------------------------------------------------------------------ observation structure
     def _structure(self, flat):
         """flat: torch [E,D] (batched face) or numpy [D] (single-env face) -> Dict / Box observation."""
@@ -323,10 +401,16 @@ class EvacuationEnv:
         """env.py:106-139.  `seed` re-keys the Philox streams (rng="philox"); like in the reference
         it does NOT touch the global NumPy stream that rng="numpy" draws from."""
         lib = nat.load()
+        if self.save_next_episode_anim or (self.time.n_episodes + 1) % self.giff_freq == 0:  # env.py:110-112
+            self.draw = True
+            self.save_next_episode_anim = True
+        if self.time.n_episodes > 0 and self._h is not None and not self.batched:
+            self.last_episode_log = self._log_finished_episode()
         if seed is not None and self.rng == "philox" and int(seed) != self.seed_value:
             self.close()
             self.seed_value = int(seed)
         h = self._handle()
+        self.time.n_episodes += 1
         E, N = self.num_envs, self.cfg.number_of_pedestrians
         if self.rng == "philox":
             nat.check(lib.evac_reset(h, None, _ptr(self._obs), self._stream()))
@@ -342,6 +426,10 @@ class EvacuationEnv:
                            agent_direction=np.zeros((E, 2), np.float32), now=np.zeros(E, np.int32))
             nat.check(lib.evac_observe(h, _ptr(self._obs), self._stream()))
         self._host_statuses = None
+        if self.draw:
+            self.pedestrians.memory = {"positions": [], "statuses": []}
+            self.agent.memory = {"position": []}
+            self.pedestrians.save()
         return self._emit_obs(), {}
 
     def _numpy_noise(self):
@@ -378,6 +466,9 @@ class EvacuationEnv:
                                     _ptr(self._terminated), _ptr(self._truncated), self._stream()))
             if self.rng == "numpy":
                 self._host_statuses = None
+            if self.draw:  # env.py:153-155 (host copies of the tracked environment; off by default)
+                self.pedestrians.save()
+                self.agent.save()
             return (self._obs_view, self._reward, self._terminated_b, self._truncated_b, {})
         # ---- single-env face: host buffers through evac_step_host
         act = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(E, 2))
@@ -402,6 +493,14 @@ class EvacuationEnv:
                                      _ptr(hb["obs"]), _ptr(hb["rew"]), _ptr(hb["term"]), _ptr(hb["trunc"])))
         if self.rng == "numpy":
             self._host_statuses = self.get_state()["statuses"].cpu().numpy()
+        if self.draw:
+            self.pedestrians.save()
+            self.agent.save()
+            if E == 1 and (bool(term[0]) or bool(trunc[0])):  # env.py:164-165
+                try:
+                    self.save_animation()
+                except ImportError as exc:
+                    log.warning("animation skipped: %s", exc)
         if E == 1:
             return self._structure(obs[0]), float(rew[0]), bool(term[0]), bool(trunc[0]), {}
         return self._structure(obs), rew, term.astype(bool), trunc.astype(bool), {}
@@ -439,11 +538,67 @@ class EvacuationEnv:
         nat.check(lib.evac_episode_stats(h, _ptr(stats), _ptr(fin), _ptr(tot), self._stream()))
         return stats, fin.bool(), tot
 
+    # ------------------------------------------------------------------ rendering (env.py:173-324), host-side
+    _STATUS_COLORS = {1: "tab:blue", 2: "tab:green", 3: "tab:orange", 4: "tab:gray"}  # viscek, follower, exiting, escaped
+
+    def _matplotlib(self):
+        try:
+            import matplotlib
+
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+            from matplotlib import animation
+        except ImportError as exc:  # not installed in the B200 image
+            raise ImportError("render / save_animation need matplotlib, which is not installed; the recorded trajectory is "
+                              "available as env.unwrapped.pedestrians.memory / agent.memory") from exc
+        return plt, animation
+
+    def _draw_frame(self, ax, positions, statuses, agent_position):
+        w, h = self.area.width, self.area.height
+        ax.clear()
+        ax.set_xlim(-1.1 * w, 1.1 * w); ax.set_ylim(-1.1 * h, 1.1 * h); ax.set_aspect("equal")
+        ax.plot([-w, w, w, -w, -w], [-h, -h, h, h, -h], color="black", linewidth=1)
+        from matplotlib.patches import Circle
+
+        ex = self.area.exit.position
+        ax.add_patch(Circle((ex[0], ex[1]), SwitchDistances.to_exit, alpha=0.15, color="tab:orange"))
+        ax.add_patch(Circle(tuple(agent_position), SwitchDistances.to_leader, alpha=0.15, color="tab:green"))
+        for code, color in self._STATUS_COLORS.items():
+            m = statuses == code
+            ax.scatter(positions[m, 0], positions[m, 1], s=12, color=color)
+        ax.scatter([agent_position[0]], [agent_position[1]], s=40, color="red", marker="*")
+
     def render(self):
-        raise NotImplementedError("rendering is out of scope of the B200 hot path (DESIGN.md)")
+        """PNG of the tracked environment's current state into `path_png` (env.py:173-240)."""
+        plt, _ = self._matplotlib()
+        st = self.get_state()
+        e = self.tracked_env
+        fig, ax = plt.subplots(figsize=(5, 5))
+        self._draw_frame(ax, st["positions"][e].cpu().numpy(), st["statuses"][e].cpu().numpy(), st["agent_position"][e].cpu().numpy())
+        os.makedirs(self.path_png, exist_ok=True)
+        path = os.path.join(self.path_png, f"{self.experiment_name}_ep{self.time.n_episodes}_t{int(st['now'][e])}.png")
+        fig.savefig(path)
+        plt.close(fig)
+        return path
 
     def save_animation(self):
-        raise NotImplementedError("rendering is out of scope of the B200 hot path (DESIGN.md)")
+        """GIF of the recorded trajectory (`draw=True`) into `path_giff` (env.py:241-324)."""
+        plt, animation = self._matplotlib()
+        pos, sts, ag = self.pedestrians.memory["positions"], self.pedestrians.memory["statuses"], self.agent.memory["position"]
+        if not pos:
+            raise RuntimeError("no trajectory recorded: construct the env with draw=True (or set env.unwrapped.draw) before reset()")
+        fig, ax = plt.subplots(figsize=(5, 5))
+
+        def frame(t):
+            self._draw_frame(ax, pos[t], sts[t], ag[max(t - 1, 0)] if ag else np.zeros(2))
+
+        anim = animation.FuncAnimation(fig, frame, frames=len(pos), interval=20)
+        os.makedirs(self.path_giff, exist_ok=True)
+        path = os.path.join(self.path_giff, f"{self.experiment_name}_ep{self.time.n_episodes}.gif")
+        anim.save(path, writer=animation.PillowWriter(fps=25))
+        plt.close(fig)
+        self.draw, self.save_next_episode_anim = bool(self.cfg.draw), False
+        return path
 
 
 __all__ = ["EvacuationEnv", "Status"]

@@ -183,6 +183,11 @@ int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const flo
  * their statistics since creation -- the vector that is all-gathered across ranks. */
 int evac_episode_stats(EvacHandle* h, float* stats, uint8_t* finished, double* totals, void* stream);
 
+/* Running accumulators of the CURRENT episode of every env (env.py:65-67,168-170) and the overall step counter
+ * (area.py:42-59): acc [E,3] float64 = episode_reward, episode_intrinsic_reward, episode_status_reward;
+ * overall_timesteps [E] int64.  Device pointers; either may be NULL. */
+int evac_get_accumulators(EvacHandle* h, double* acc, int64_t* overall_timesteps, void* stream);
+
 /* Number of kernels this library launched since the handle was created. */
 int64_t evac_launch_count(const EvacHandle* h);
 

@@ -8,6 +8,8 @@ differ when the float64 quantity sits within ~1e-7 of its threshold; the oracle 
 distance (`StepInfo.margin`) and such steps are excluded from the bit-exact assertion and
 COUNTED (near-threshold protocol).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -187,19 +189,20 @@ def test_free_running_episode_parity(name):
 @pytest.mark.parametrize("n,num_envs,steps", [(1, 7, 3), (2, 5, 3), (31, 3, 3), (32, 3, 3), (64, 4, 3), (65, 3, 2), (128, 2, 2), (129, 2, 2),
                                               (257, 2, 2), (600, 2, 2), (1500, 1, 1), (4096, 1, 1)])
 @pytest.mark.parametrize("wrap", [dict(positions="rel", statuses="ohe", type="Box"), dict(positions="grav", alpha=2)])
-@pytest.mark.parametrize("search", ["auto", "brute"])
+@pytest.mark.parametrize("search", ["auto", "other"])
 def test_kernel_shapes_random_states(n, num_envs, steps, wrap, search):
-    """All CTA shapes (THREADS x PPT), ragged N, random layouts, both neighbour searches (N > 64: "auto" = cell
-    list, "brute" = all-pairs tiles): teacher-forced against the oracle."""
-    if n <= 64 and search == "brute":
-        pytest.skip("N <= 64 always runs the one-warp all-pairs tile")
+    """All CTA shapes (THREADS x PPT), ragged N, random layouts, both neighbour searches ("auto" = all-pairs warp tile
+    for N <= 64 / cell list above; "other" = strip-culled warp tile for N <= 64 / all-pairs tiles above):
+    teacher-forced against the oracle."""
+    if search == "other":
+        search = "cells" if n <= 64 else "brute"
     rs = np.random.RandomState(n)
     env_kw = dict(number_of_pedestrians=n, is_new_exiting_reward=True, intrinsic_reward_coef=0.3, enslaving_degree=0.7)
     cfg = OracleConfig(**env_kw, **wrap)
     env = _make_env(env_kw, wrap, num_envs, neighbor_search=search)
     u = env.unwrapped
     u.reset()
-    assert (u.num_cells > 0) == (n > 64 and search == "auto")
+    assert (u.num_cells > 0) == ((n > 64) == (search == "auto"))
     oracles = []
     for e in range(num_envs):
         o = OracleEnv(cfg)
@@ -232,7 +235,7 @@ def test_kernel_shapes_random_states(n, num_envs, steps, wrap, search):
             _assert_obs_close(wrap, flat[e], flatten_observation(oobs), rtol=5e-5)
 
 
-@pytest.mark.parametrize("n,width,height,vision", [(4096, 1.0, 1.0, 0.1), (1000, 1.5, 0.8, 0.1), (300, 1.0, 1.0, 0.35), (2048, 1.0, 1.0, 0.011), (200, 1.0, 1.0, 0.9),
+@pytest.mark.parametrize("n,width,height,vision", [(60, 1.0, 1.0, 0.1), (64, 1.5, 0.8, 0.1), (33, 1.0, 1.0, 0.3), (4096, 1.0, 1.0, 0.1), (1000, 1.5, 0.8, 0.1), (300, 1.0, 1.0, 0.35), (2048, 1.0, 1.0, 0.011), (200, 1.0, 1.0, 0.9),
                                                    (500, 0.3, 0.3, 0.1)])
 def test_cell_list_equals_all_pairs_search(n, width, height, vision, monkeypatch):
     """Large crowds (BASELINE config 4): the cell-list neighbour search evaluates the same predicate on a superset
@@ -485,3 +488,44 @@ def test_error_behaviour_matches_reference():
     obs, _ = env.reset()
     assert set(obs) == {"agent_position", "pedestrians_positions", "exit_position"}
     assert obs["pedestrians_positions"].shape == (10, 2)
+
+
+def test_logging_and_trajectory_capture(tmp_path):
+    """`draw` records the tracked environment's trajectory like Pedestrians.save / Agent.save, reset() logs
+    the finished episode with the reference's keys (env.py:115-125), rendering needs matplotlib (absent here -> ImportError)."""
+    import evacuation_b200 as eb
+
+    n = 10
+    cfg = eb.EnvConfig(number_of_pedestrians=n, draw=True, wandb_enabled=False, path_logs=str(tmp_path / "logs"), path_giff=str(tmp_path / "giff"),
+                       path_png=str(tmp_path / "png"), is_new_exiting_reward=True, intrinsic_reward_coef=1.0, experiment_name="t")
+    np.random.seed(3)
+    env = eb.setup_env(cfg, eb.EnvWrappersConfig())
+    u = env.unwrapped
+    env.reset()
+    oracle = OracleEnv(OracleConfig(number_of_pedestrians=n, is_new_exiting_reward=True, intrinsic_reward_coef=1.0))
+    st = u.get_state()
+    oracle.set_state(st["positions"][0].cpu().numpy(), st["directions"][0].cpu().numpy(), st["statuses"][0].cpu().numpy(), np.zeros(2, np.float32))
+    total = 0.0
+    for t in range(6):
+        a = np.array([np.sin(0.3 * t), np.cos(0.3 * t)], dtype=np.float32)
+        noise = np.random.RandomState(t).uniform(-0.1, 0.1, n).astype(np.float32)
+        _, r, _, _, _ = env.step(a, noise=noise)
+        _, ro, _, _, _ = oracle.step(a.copy(), noise.astype(np.float64))
+        total += ro
+        assert abs(r - ro) <= 1e-5 * max(1.0, abs(ro))
+    assert len(u.pedestrians.memory["positions"]) == 7 and len(u.pedestrians.memory["statuses"]) == 7 and len(u.agent.memory["position"]) == 6
+    np.testing.assert_allclose(u.pedestrians.memory["positions"][-1], oracle.positions, atol=2e-6)
+    d = u.episode_log()
+    assert list(d) == list(eb._native.EPISODE_STAT_KEYS)
+    assert d["episode_length"] == 6 and d["overall_timesteps"] == 6 and abs(d["episode_reward"] - total) <= 1e-4 * abs(total)
+    assert d["escaped_pedestrians"] + d["exiting_pedestrians"] + d["following_pedestrians"] + d["viscek_pedestrians"] == n
+    try:
+        import matplotlib  # noqa: F401
+        assert os.path.exists(u.save_animation())
+    except ImportError:
+        with pytest.raises(ImportError):
+            u.save_animation()
+    env.reset()  # logs the finished episode like env.py:114-127
+    assert u.last_episode_log["episode_length"] == 6 and u.time.n_episodes == 2
+    logfile = tmp_path / "logs" / "logs_t.log"
+    assert logfile.exists() and "episode_reward=" in logfile.read_text()

@@ -14,6 +14,6 @@ timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_
 timeout 300 python tools/probe.py > $OUT/probe.json 2>&1; cat $OUT/probe.json
 timeout 300 python tools/quick_bench.py > $OUT/quick_bench.jsonl 2>&1; cat $OUT/quick_bench.jsonl
 kill $SMI
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu > $OUT/bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:evac_step_kernel -s 5 -c 2 -o $OUT/prof_step python bench.py --steps 20 --warmup 3 --no-cpu > $OUT/ncu_full.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu --no-extra > $OUT/bench_under_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:evac_ -s 8 -c 2 -o $OUT/prof_step python bench.py --steps 20 --warmup 3 --no-cpu --no-extra > $OUT/ncu_full.log 2>&1
 ls -la $OUT

@@ -103,10 +103,28 @@ class _SetAttention(nn.Module):
         def split(t):  # [B, S, H*D] -> [B, D, S, H]
             return t.view(B, S, H, D).permute(0, 3, 1, 2)
 
-        q, k, v = split(self.Wq(x)), split(self.Wk(x)), split(self.Wv(x))
-        out = F.scaled_dot_product_attention(q, k, v, scale=1.0 / math.sqrt(D))  # [B, D, S, H], scores never hit HBM
+        # one GEMM for the three projections (K = 6 GEMMs are launch / tail bound); parameter names stay the reference's
+        qkv = F.linear(x, torch.cat([self.Wq.weight, self.Wk.weight, self.Wv.weight]), torch.cat([self.Wq.bias, self.Wk.bias, self.Wv.bias]))
+        q, k, v = (split(t) for t in qkv.split(H * D, dim=-1))
+        if x.is_cuda:
+            # zero-padding the contracted axis (H = 3) to 8 changes neither the scores nor the outputs but lets SDPA take
+            # its fused kernel instead of the batched-GEMM + softmax fallback (2.6 -> 1.1 ms at 8192 envs on B200)
+            pad = (-H) % 8
+            q, k, v = (F.pad(t, (0, pad)) for t in (q, k, v))
+            out = F.scaled_dot_product_attention(q, k, v, scale=1.0 / math.sqrt(D))[..., :H]
+        else:
+            out = F.scaled_dot_product_attention(q, k, v, scale=1.0 / math.sqrt(D))  # [B, D, S, H]
         out = out.transpose(1, 2).reshape(B, S, D * H)
         return self.dense(out)
+
+
+def _layer_norm(x, ln: nn.LayerNorm):
+    """LayerNorm over a 6-wide last axis written as elementwise ops: torch's row-wise kernel launches one block per
+    row and takes 2.2 ms for the 5e5 rows of an 8192-env batch (half of the whole policy forward on B200)."""
+    mu = x.mean(dim=-1, keepdim=True)
+    xc = x - mu
+    var = (xc * xc).mean(dim=-1, keepdim=True)
+    return xc * torch.rsqrt(var + ln.eps) * ln.weight + ln.bias
 
 
 class _Block(nn.Module):
@@ -126,9 +144,9 @@ class _Block(nn.Module):
         if x.dim() == 2:
             x = x.view(shape[0], -1, self.d_model)
         a = self.dropout(self.attention(x))
-        x = self.norm1(x + a if self.use_resid else a)
+        x = _layer_norm(x + a if self.use_resid else a, self.norm1)
         f = self.dropout(self.ff(x))
-        x = self.norm2(x + f if self.use_resid else f)
+        x = _layer_norm(x + f if self.use_resid else f, self.norm2)
         return x.view(shape)
 
 

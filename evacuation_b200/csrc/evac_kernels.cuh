@@ -57,8 +57,8 @@ struct KArgs {
   real thr2_ped, thr2_leader, thr2_exit, thr2_escape;
   // uniform cell grid of the neighbour search (multi-warp shapes, float32): cells_x * cells_y cells of edge
   // >= vision radius over [-width,width] x [-height,height]; cells_x == 0 -> brute-force tiled pass
-  int cells_x, cells_y;
-  float cell_inv_x, cell_inv_y;  // cells per unit length
+  int cells_x, cells_y, cell_reach;  // neighbours within `cell_reach` cells (cell edge >= radius / cell_reach)
+  float cell_inv_x, cell_inv_y;      // cells per unit length
   int exit_reward, follow_reward, term_wall;
   real init_reward, intrinsic_coef;
   int max_timesteps;
@@ -389,11 +389,12 @@ __device__ __forceinline__ void cell_list_pass(const Tile<float>& tile, const Ce
     const float x = (s & 1) ? pp.y : pp.x, y = (s & 1) ? pp.w : pp.z;
     int cx, cy;
     cell_of(x, y, a, cx, cy);
-    const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, a.cells_x - 1);
+    const int reach = a.cell_reach;
+    const int cx0 = max(cx - reach, 0), cx1 = min(cx + reach, a.cells_x - 1);
     const float2 nx = make_float2(-x, -x), ny = make_float2(-y, -y);
     float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
     int done = 0;  // even slot index below which everything has been evaluated already
-    for (int row = max(cy - 1, 0); row <= min(cy + 1, a.cells_y - 1); ++row) {
+    for (int row = max(cy - reach, 0); row <= min(cy + reach, a.cells_y - 1); ++row) {
       const int lo = max(cs.cell_start[row * a.cells_x + cx0] & ~1, done);
       const int hi = (cs.cell_start[row * a.cells_x + cx1 + 1] + 1) & ~1;
       int j = lo >> 1;

@@ -529,3 +529,70 @@ def test_logging_and_trajectory_capture(tmp_path):
     assert u.last_episode_log["episode_length"] == 6 and u.time.n_episodes == 2
     logfile = tmp_path / "logs" / "logs_t.log"
     assert logfile.exists() and "episode_reward=" in logfile.read_text()
+
+
+def _status_from_positions(pos, agent_pos, thr):
+    """statuses.py:29-48 in float64 torch on the device: FOLLOWER < 0.2 of the agent, EXITING < 0.4 / ESCAPED < 0.01 of the exit."""
+    p = pos.double()
+    da = (p - agent_pos.double()[:, None, :]).norm(dim=-1)
+    de = (p - torch.tensor([0.0, -1.0], dtype=torch.float64, device=pos.device)).norm(dim=-1)
+    st = torch.ones_like(da, dtype=torch.uint8)
+    st[da < thr["leader"]] = 2
+    st[de < thr["exit"]] = 3
+    st[de < thr["escape"]] = 4
+    margin = torch.minimum(torch.minimum((da - thr["leader"]).abs(), (de - thr["exit"]).abs()), (de - thr["escape"]).abs())
+    return st, margin
+
+
+@pytest.mark.parametrize("label,E,n,wrap,steps", [
+    ("C2", 4096, 60, dict(positions="rel", statuses="ohe", type="Box"), 300),
+    ("C3", 4096, 60, dict(positions="grav", alpha=4), 300),
+    ("C4", 256, 4096, dict(positions="rel", statuses="ohe", type="Box"), 25),
+    ("C5", 65536, 60, dict(positions="rel", statuses="ohe", type="Box"), 60),
+])
+def test_full_size_invariants(label, E, n, wrap, steps):
+    """BASELINE.json's full sizes through size-independent properties: positions stay in the arena, the
+    status is a pure function of (position, agent position), escaped pedestrians are pinned to the exit with a zero
+    direction from the following step on, ESCAPED is absorbing, rewards / observations are finite, the observation
+    is consistent with the state, and a batch split over two handles (two 'ranks') equals the whole batch bit for bit."""
+    import evacuation_b200 as eb
+
+    env_kw = dict(number_of_pedestrians=n, is_new_exiting_reward=True, intrinsic_reward_coef=0.1, enslaving_degree=0.5, noise_coef=0.5)
+    mk = lambda num, off: eb.setup_env(eb.EnvConfig(**env_kw), eb.EnvWrappersConfig(**wrap), num_envs=num, seed=11, auto_reset=False,
+                                       env_index_offset=off)
+    env, lo, hi = mk(E, 0), mk(E // 2, 0), mk(E - E // 2, E // 2)
+    for e_ in (env, lo, hi):
+        e_.reset()
+    u = env.unwrapped
+    thr = dict(leader=0.2, exit=0.4, escape=0.01)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    prev_st = u.get_state()["statuses"].clone()
+    for t in range(steps):
+        actions = torch.rand((E, 2), device="cuda", generator=g) * 2 - 1
+        obs, reward, term, trunc, _ = env.step(actions)
+        lo.step(actions[: E // 2].contiguous())
+        hi.step(actions[E // 2:].contiguous())
+        if t % 10 != 9 and t != steps - 1:
+            continue
+        st = u.get_state()
+        pos, dirs, sts, ap = st["positions"], st["directions"], st["statuses"], st["agent_position"]
+        assert torch.isfinite(pos).all() and torch.isfinite(reward).all()
+        assert (pos[..., 0].abs() <= 1.0).all() and (pos[..., 1].abs() <= 1.0).all() and (ap.abs() <= 1.0).all()
+        want, margin = _status_from_positions(pos, ap, thr)
+        clear = margin > 1e-6
+        assert torch.equal(sts[clear], want[clear]), f"{label}: status is not f(position, agent) at step {t}"
+        was_escaped = prev_st == 4
+        assert (sts[was_escaped] == 4).all(), "ESCAPED must be absorbing"
+        assert (pos[was_escaped] == torch.tensor([0.0, -1.0], device="cuda")).all() and (dirs[was_escaped] == 0).all()
+        assert (dirs.norm(dim=-1) <= 0.01 * (1 + 1e-5)).all(), "|direction| <= step_size"
+        assert bool(((sts == 4).sum(dim=1) == n).eq(term).all())
+        if wrap["positions"] == "rel":  # observation rows = [agent; exit; pedestrians], relative / sqrt(2), one-hot of 4 - status
+            o = obs.reshape(E, n + 2, 6)
+            torch.testing.assert_close(o[:, 0, :2], ap)
+            torch.testing.assert_close(o[:, 2:, :2], (pos - ap[:, None, :]) / 1.41421353816986083984375, rtol=1e-6, atol=1e-7)
+            assert torch.equal(o[:, 2:, 2:].argmax(dim=-1), (4 - sts.long())) and (o[:, 2:, 2:].sum(dim=-1) == 1).all()
+        prev_st = sts.clone()
+    whole = u.get_state()
+    for key in ("positions", "directions", "statuses", "agent_position"):
+        parts = torch.cat([lo.unwrapped.get_state()[key], hi.unwrapped.get_state()[key]])
+        assert torch.equal(whole[key], parts), f"{label}: sharded batch differs from the whole batch in {key}"

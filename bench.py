@@ -377,25 +377,37 @@ def other_workloads(dev):
     out["c4_large_crowd_256x4096_cells"] = rollout_us(dict(number_of_pedestrians=4096), WRAP_KW, 256, 20)
     out["c4_large_crowd_256x4096_all_pairs"] = rollout_us(dict(number_of_pedestrians=4096), WRAP_KW, 256, 4, neighbor_search="brute")
     out["c5_env_only_65536x60"] = rollout_us(ENV_KW, WRAP_KW, 65536, 100)
-    # config 5, one rank's share of the 8-GPU job (65536 / 8 envs) with the policy in the loop
-    from evacuation_b200.rollout import PolicyRollout, RPOTransformerPolicy
+    # config 5, one rank's share of the 8-GPU job (65536 / 8 envs) with the policy in the loop: the fused CUDA policy
+    # (evac_policy_forward: embedding kernel + heads kernel, NormalizeObservation / ClipAction fused) and, beside it, the
+    # same loop with the PyTorch restatement of the policy (library GEMMs / SDPA)
+    from evacuation_b200.rollout import FusedRPOTransformerPolicy, PolicyRollout, RPOTransformerPolicy
 
-    E = 8192
-    env = eb.setup_env(eb.EnvConfig(**ENV_KW), eb.EnvWrappersConfig(**WRAP_KW), num_envs=E, device=dev, seed=7, auto_reset=True)
-    torch.manual_seed(1)
-    ro = PolicyRollout(env, RPOTransformerPolicy(env.unwrapped.obs_dim, N_PED).to(dev), use_graph=True, store=False)
-    ro.reset()
-    ro.run(4)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
-    e0.record()
-    ro.run(8)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / 8
-    out["c5_policy_loop_8192x60"] = {"envs": E, "pedestrians": N_PED, "ms_per_step": ms, "pedestrian_steps_per_s": E * N_PED / ms * 1e3,
-                                     "note": "RPO transformer-embedding policy forward (PyTorch, random init) -> ClipAction -> fused env step -> "
-                                             "Normalize{Observation,Reward}, CUDA-graph replayed; the policy is >99 % of the loop"}
+    def policy_loop_ms(E, fused, steps):
+        env = eb.setup_env(eb.EnvConfig(**ENV_KW), eb.EnvWrappersConfig(**WRAP_KW), num_envs=E, device=dev, seed=7, auto_reset=True)
+        torch.manual_seed(1)
+        net = RPOTransformerPolicy(env.unwrapped.obs_dim, N_PED).to(dev)  # train mode: dropout active like the reference's rollouts
+        pol = FusedRPOTransformerPolicy(net, N_PED, device=dev, seed=1) if fused else net
+        ro = PolicyRollout(env, pol, use_graph=True, store=False)
+        ro.reset()
+        ro.run(4)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        ro.run(steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        assert bool(torch.isfinite(ro.out["value"]).all())
+        env.unwrapped.close()
+        return ms
+
+    for E, fused, steps, key in ((8192, True, 64, "c5_policy_loop_8192x60"), (65536, True, 16, "c5_policy_loop_65536x60"),
+                                 (8192, False, 8, "c5_policy_loop_8192x60_torch_policy")):
+        ms = policy_loop_ms(E, fused, steps)
+        out[key] = {"envs": E, "pedestrians": N_PED, "ms_per_step": ms, "pedestrian_steps_per_s": E * N_PED / ms * 1e3, "env_steps_per_s": E / ms * 1e3,
+                    "note": ("fused CUDA policy (evac_policy_forward: NormalizeObservation + 2 transformer blocks, heads + Normal sampling + ClipAction) "
+                             "-> fused env step -> evac_normalize_reward: 4 launches per iteration, CUDA-graph replayed, dropout active") if fused else
+                            "the same loop with the PyTorch restatement of the policy (library GEMMs / SDPA), CUDA-graph replayed"}
     return out
 
 

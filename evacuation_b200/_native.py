@@ -10,7 +10,7 @@ import os
 
 from .build import LIB_PATH
 
-EVAC_ABI_VERSION = 2
+EVAC_ABI_VERSION = 3
 NUM_EPISODE_STATS = 9
 EPISODE_STAT_KEYS = (  # env.py:115-125
     "episode_intrinsic_reward", "episode_status_reward", "episode_reward", "episode_length",
@@ -45,6 +45,26 @@ class EvacConfig(C.Structure):
     ]
 
 
+class EvacPolicyConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("seq_len", C.c_int32), ("d_model", C.c_int32), ("num_heads", C.c_int32),
+        ("dim_feedforward", C.c_int32), ("num_blocks", C.c_int32), ("use_resid", C.c_int32),
+        ("dropout", C.c_float), ("layer_norm_eps", C.c_float), ("num_hidden", C.c_int32), ("action_dim", C.c_int32),
+    ]
+
+
+class EvacPolicyIO(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("obs", C.c_void_p),
+        ("norm_mean", C.c_void_p), ("norm_var", C.c_void_p), ("norm_count", C.c_void_p), ("obs_norm", C.c_void_p),
+        ("norm_eps", C.c_float), ("norm_clip", C.c_float),
+        ("embedding", C.c_void_p), ("mean", C.c_void_p), ("value", C.c_void_p), ("action", C.c_void_p),
+        ("action_clipped", C.c_void_p), ("logprob", C.c_void_p), ("entropy", C.c_void_p), ("given_action", C.c_void_p),
+        ("sample", C.c_int32), ("training", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("offset_device", C.c_void_p), ("env_index_offset", C.c_int64),
+    ]
+
+
 # every symbol include/evac_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -67,6 +87,15 @@ SIGNATURES = {
     "evac_episode_stats": (C.c_int, [_P, _P, _P, _P, _P]),
     "evac_get_accumulators": (C.c_int, [_P, _P, _P, _P]),
     "evac_launch_count": (C.c_int64, [_P]),
+    "evac_policy_default_config": (C.c_int, [C.POINTER(EvacPolicyConfig), C.c_int32, C.c_int32]),
+    "evac_policy_create": (C.c_int, [C.POINTER(EvacPolicyConfig), C.c_int32, C.POINTER(_P)]),
+    "evac_policy_destroy": (C.c_int, [_P]),
+    "evac_policy_num_weights": (C.c_int64, [_P]),
+    "evac_policy_load_weights": (C.c_int, [_P, _P, C.c_int64]),
+    "evac_policy_reserve": (C.c_int, [_P, C.c_int32]),
+    "evac_policy_forward": (C.c_int, [_P, C.POINTER(EvacPolicyIO), _P]),
+    "evac_policy_launch_count": (C.c_int64, [_P]),
+    "evac_normalize_reward": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P]),
     "evac_probe_fma": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "evac_probe_pairwise": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
 }

@@ -9,11 +9,11 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libevac_b200.so")
-SOURCES = [os.path.join(CSRC, "evac_abi.cu")]
-HEADERS = [os.path.join(CSRC, "evac_kernels.cuh"), os.path.join(CSRC, "philox.cuh"),
-           os.path.join(os.path.dirname(PKG_DIR), "include", "evac_b200.h")]
+SOURCES = [os.path.join(CSRC, "evac_abi.cu"), os.path.join(CSRC, "evac_policy.cu")]
+HEADERS = [os.path.join(CSRC, "evac_kernels.cuh"), os.path.join(CSRC, "evac_warp.cuh"), os.path.join(CSRC, "philox.cuh"),
+           os.path.join(CSRC, "evac_policy.cuh"), os.path.join(os.path.dirname(PKG_DIR), "include", "evac_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"]
 
 
 def find_nvcc() -> str:
@@ -34,15 +34,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libevac_b200.so next to this file (cross-compiles without a GPU)."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = find_nvcc()
+    objs, procs = [], []
+    for src in SOURCES:  # one nvcc per translation unit, in parallel
+        obj = os.path.join(CSRC, os.path.splitext(os.path.basename(src))[0] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas=-v"] if verbose else []), "-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        objs.append(obj)
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for cmd, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{out}\n{err}")
+        if verbose:
+            print(err, file=sys.stderr)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB_PATH, *objs], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr, file=sys.stderr)
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     return LIB_PATH
 
 

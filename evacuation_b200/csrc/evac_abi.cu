@@ -27,6 +27,12 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// other translation units of this library (evac_policy.cu) report through the same thread-local message
+int evac_set_error_(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \

@@ -190,6 +190,160 @@ class RPOTransformerPolicy(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------
+_FLAT_BLOCK_KEYS = ("attention.Wq.weight", "attention.Wq.bias", "attention.Wk.weight", "attention.Wk.bias",
+                    "attention.Wv.weight", "attention.Wv.bias", "attention.dense.weight", "attention.dense.bias",
+                    "ff.0.weight", "ff.0.bias", "ff.3.weight", "ff.3.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")
+_FLAT_HEAD_KEYS = ("critic.0.weight", "critic.0.bias", "critic.2.weight", "critic.2.bias", "critic.4.weight", "critic.4.bias",
+                   "actor_mean.0.weight", "actor_mean.0.bias", "actor_mean.2.weight", "actor_mean.2.bias",
+                   "actor_mean.4.weight", "actor_mean.4.bias", "actor_logstd")
+
+
+def flatten_policy_weights(state_dict, num_blocks: int):
+    """The reference module's `state_dict()` -> the flat float32 vector `evac_policy_load_weights` documents
+    (include/evac_b200.h).  Works on the unmodified reference `RPOTransformerEmbedding` and on `RPOTransformerPolicy`."""
+    parts = [state_dict[f"embedding.{b}.{k}"] for b in range(num_blocks) for k in _FLAT_BLOCK_KEYS]
+    parts += [state_dict[k] for k in _FLAT_HEAD_KEYS]
+    return torch.cat([p.detach().to(torch.float32).reshape(-1).cpu() for p in parts]).contiguous()
+
+
+class FusedRPOTransformerPolicy:
+    """Forward-only CUDA implementation of `RPOTransformerPolicy` (= the reference's `RPOTransformerEmbedding`):
+    two hand-written kernels behind `evac_policy_forward` (csrc/evac_policy.cuh) instead of ~60 library launches --
+    the transformer blocks run one warp per environment out of registers, the actor / critic heads 32 environments
+    per CTA, Normal sampling, log-probability and ClipAction included.  Optionally fuses the per-env
+    NormalizeObservation + clip of `VectorNormalizer` into its prologue (`normalizer=`).
+
+    Weights are snapshotted from a torch module (`load_from`); call it again after an optimiser step.  There is no
+    CPU fallback: construction fails without the CUDA library / a device."""
+
+    def __init__(self, module: "RPOTransformerPolicy", number_of_pedestrians: int, device="cuda", seed: int = 0,
+                 env_index_offset: int = 0, max_envs: int = 0):
+        import ctypes as C
+
+        from . import _native as nat
+
+        self._C, self._nat, self._lib = C, nat, nat.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nat.EvacNativeError("FusedRPOTransformerPolicy needs a CUDA device (no CPU fallback)")
+        blk = module.embedding[0]
+        self.S, self.D = number_of_pedestrians + 2, blk.d_model
+        self.A = module.actor_mean[4].out_features
+        cfg = nat.EvacPolicyConfig()
+        nat.check(self._lib.evac_policy_default_config(C.byref(cfg), number_of_pedestrians, self.D))
+        cfg.num_heads, cfg.dim_feedforward = blk.attention.num_heads, blk.ff[0].out_features
+        cfg.num_blocks, cfg.use_resid = len(module.embedding), int(blk.use_resid)
+        cfg.dropout, cfg.layer_norm_eps = float(blk.dropout.p), float(blk.norm1.eps)
+        cfg.num_hidden, cfg.action_dim = module.critic[0].out_features, self.A
+        self.cfg, self.num_blocks = cfg, cfg.num_blocks
+        self.seed, self.env_index_offset = int(seed), int(env_index_offset)
+        self._h = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        nat.check(self._lib.evac_policy_create(C.byref(cfg), idx, C.byref(self._h)))
+        self.calls = torch.zeros((), dtype=torch.int64, device=self.device)  # device-side stream offset (graph-replay safe)
+        self.training = True  # like the reference's rollouts (the module is never put in eval mode)
+        self.load_from(module)
+        if max_envs:
+            nat.check(self._lib.evac_policy_reserve(self._h, int(max_envs)))
+
+    def load_from(self, module) -> None:
+        flat = flatten_policy_weights(module.state_dict(), self.num_blocks)
+        want = self._lib.evac_policy_num_weights(self._h)
+        if flat.numel() != want:
+            raise ValueError(f"policy weights: expected {want} floats, module has {flat.numel()}")
+        self._nat.check(self._lib.evac_policy_load_weights(self._h, flat.data_ptr(), flat.numel()))
+
+    def train(self, mode: bool = True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def reserve(self, max_envs: int) -> None:
+        self._nat.check(self._lib.evac_policy_reserve(self._h, int(max_envs)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.evac_policy_launch_count(self._h))
+
+    def _ptr(self, t, dtype=torch.float32):
+        if t is None:
+            return None
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == dtype):
+            raise ValueError(f"expected a contiguous CUDA {dtype} tensor, got {t.dtype} on {t.device}")
+        return t.data_ptr()
+
+    def forward(self, obs, *, embedding=None, mean=None, value=None, action=None, action_clipped=None, logprob=None, entropy=None,
+                given_action=None, sample=True, normalizer: Optional["VectorNormalizer"] = None, obs_norm=None, advance=True):
+        """One fused forward on the current stream; every output is an optional preallocated tensor."""
+        E = obs.shape[0]
+        if obs.numel() != E * self.S * self.D:
+            raise ValueError(f"obs must hold [E, {self.S * self.D}] values, got {tuple(obs.shape)}")
+        io = self._nat.EvacPolicyIO()
+        io.num_envs, io.obs = E, self._ptr(obs)
+        if normalizer is not None:
+            io.norm_mean, io.norm_var = self._ptr(normalizer.obs_mean), self._ptr(normalizer.obs_var)
+            io.norm_count, io.obs_norm = self._ptr(normalizer.obs_count, torch.float64), self._ptr(obs_norm)
+            io.norm_eps, io.norm_clip = normalizer.epsilon, normalizer.obs_clip
+        io.embedding, io.mean, io.value = self._ptr(embedding), self._ptr(mean), self._ptr(value)
+        io.action, io.action_clipped = self._ptr(action), self._ptr(action_clipped)
+        io.logprob, io.entropy, io.given_action = self._ptr(logprob), self._ptr(entropy), self._ptr(given_action)
+        io.sample, io.training = int(sample), int(self.training)
+        io.seed, io.offset, io.offset_device = self.seed, 0, self.calls.data_ptr()
+        io.env_index_offset = self.env_index_offset
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self._nat.check(self._lib.evac_policy_forward(self._h, self._C.byref(io), self._C.c_void_p(st)))
+        if normalizer is not None:
+            normalizer.obs_count.add_(1.0)
+        if advance:
+            self.calls.add_(1)
+
+    # ---- the reference module's surface (rpo_transformer_agent_network.py:155-163)
+    def embed(self, x):
+        out = torch.empty((x.shape[0], self.S * self.D), device=self.device)
+        self.forward(x.contiguous(), embedding=out)
+        return out
+
+    def get_value(self, x):
+        v = torch.empty(x.shape[0], device=self.device)
+        self.forward(x.contiguous(), value=v, sample=False)
+        return v.unsqueeze(1)
+
+    def get_action_and_value(self, x, action: Optional[torch.Tensor] = None):
+        """(action, logprob, entropy, value[E,1]) like the module; `action` given = evaluate its log-probability
+        (without the RPO mean perturbation, which belongs to the trainer's update pass)."""
+        E = x.shape[0]
+        o = {k: torch.empty(s, device=self.device) for k, s in (("action", (E, self.A)), ("logprob", (E,)), ("entropy", (E,)), ("value", (E,)))}
+        self.forward(x.contiguous(), given_action=None if action is None else action.contiguous(), **o)
+        return o["action"], o["logprob"], o["entropy"], o["value"].unsqueeze(1)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self._lib.evac_policy_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def normalize_reward_fused(norm: "VectorNormalizer", reward: torch.Tensor, terminated: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """`VectorNormalizer.reward` as ONE kernel (evac_normalize_reward); `terminated` is the uint8/bool flag tensor of step()."""
+    import ctypes as C
+
+    from . import _native as nat
+
+    lib = nat.load()
+    term = terminated.view(torch.uint8) if terminated.dtype == torch.bool else terminated
+    st = torch.cuda.current_stream(reward.device).cuda_stream
+    nat.check(lib.evac_normalize_reward(reward.shape[0], reward.data_ptr(), term.data_ptr(), norm.returns.data_ptr(), norm.ret_mean.data_ptr(),
+                                        norm.ret_var.data_ptr(), norm.ret_count.data_ptr(), out.data_ptr(), norm.gamma, norm.epsilon,
+                                        norm.reward_clip, C.c_void_p(st)))
+    norm.ret_count.add_(1.0)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 class PolicyRollout:
     """policy forward -> ClipAction -> fused env step (same-step auto-reset) -> normalise, `num_steps` times.
 
@@ -206,14 +360,32 @@ class PolicyRollout:
         self.out = {k: torch.zeros(s, device=self.device) for k, s in
                     (("action", (self.E, 2)), ("logprob", (self.E,)), ("value", (self.E,)), ("reward", (self.E,)))}
         self._graph = None
+        # fused policy: NormalizeObservation runs in the prologue of the policy kernel on the env's raw observation buffer,
+        # so `next_obs` (the normalised observation the policy saw) is produced INSIDE the iteration
+        self.fused = isinstance(policy, FusedRPOTransformerPolicy)
+        self._raw_obs = None
+        self._act_clipped = torch.zeros((self.E, 2), device=self.device)
+        if self.fused:
+            policy.reserve(self.E)
 
     def reset(self):
         obs, _ = self.env.reset()
-        self.next_obs.copy_(self.norm.observation(obs.reshape(self.E, self.D)))
+        if self.fused:
+            self._raw_obs = obs.reshape(self.E, self.D)  # the env's persistent observation buffer (step() rewrites it)
+        else:
+            self.next_obs.copy_(self.norm.observation(obs.reshape(self.E, self.D)))
         self.next_done.zero_()
 
     @torch.no_grad()
     def _iteration(self):
+        if self.fused:  # 4 launches: policy embedding, policy heads (+ sampling, ClipAction), env step, reward normaliser
+            self.policy.forward(self._raw_obs, normalizer=self.norm, obs_norm=self.next_obs, action=self.out["action"],
+                                action_clipped=self._act_clipped, logprob=self.out["logprob"], value=self.out["value"])
+            obs, reward, term, trunc, _ = self.env.step(self._act_clipped)
+            assert obs.data_ptr() == self._raw_obs.data_ptr()
+            normalize_reward_fused(self.norm, reward, term, self.out["reward"])
+            self.next_done.copy_(torch.logical_or(term, trunc))
+            return
         action, logprob, _, value = self.policy.get_action_and_value(self.next_obs)
         obs, reward, term, trunc, _ = self.env.step(action.clamp(-1.0, 1.0).contiguous())  # ClipAction
         self.out["action"].copy_(action); self.out["logprob"].copy_(logprob); self.out["value"].copy_(value.flatten())
@@ -244,15 +416,19 @@ class PolicyRollout:
                        dones=torch.empty((num_steps, self.E), device=self.device), values=torch.empty((num_steps, self.E), device=self.device))
         for t in range(num_steps):
             if buf is not None:
-                buf["obs"][t].copy_(self.next_obs); buf["dones"][t].copy_(self.next_done)
+                buf["dones"][t].copy_(self.next_done)
+                if not self.fused:
+                    buf["obs"][t].copy_(self.next_obs)
             if self._graph is not None:
                 self._graph.replay()
             else:
                 self._iteration()
             if buf is not None:
+                if self.fused:
+                    buf["obs"][t].copy_(self.next_obs)
                 buf["actions"][t].copy_(self.out["action"]); buf["logprobs"][t].copy_(self.out["logprob"])
                 buf["values"][t].copy_(self.out["value"]); buf["rewards"][t].copy_(self.out["reward"])
         return buf
 
 
-__all__ = ["VectorNormalizer", "RPOTransformerPolicy", "PolicyRollout"]
+__all__ = ["VectorNormalizer", "RPOTransformerPolicy", "FusedRPOTransformerPolicy", "PolicyRollout", "flatten_policy_weights", "normalize_reward_fused"]

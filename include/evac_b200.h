@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define EVAC_ABI_VERSION 2
+#define EVAC_ABI_VERSION 3
 
 enum {
   EVAC_OK = 0,
@@ -193,6 +193,87 @@ int64_t evac_launch_count(const EvacHandle* h);
 
 const char* evac_last_error(void);
 int32_t evac_abi_version(void);
+
+/* ---- rollout-loop glue for BASELINE config 5: the CALLER of step() --------------------
+ *
+ *   evac_policy_*            RPOTransformerEmbedding.get_action_and_value / get_value, forward only
+ *                                                                  src/agents/networks/rpo_transformer_agent_network.py:36-163
+ *                                                                  src/agents/networks/rpo_linear_agent_network.py:19-61
+ *                            + (optional, fused) gymnasium NormalizeObservation + clip(-1, 1), ClipAction
+ *                                                                  src/agents/rpo_agent.py:24-33,186-193
+ *   evac_normalize_reward    gymnasium NormalizeReward(gamma) + clip(-100, 100)      src/agents/rpo_agent.py:31-32
+ *
+ * The policy reads the [E, (N+2)*d_model] MatrixObs rows evac_step writes and produces the [E,2] actions evac_step
+ * consumes, so policy -> step -> normalise stays on the device (two launches for the policy, one for the step). */
+typedef struct EvacPolicyConfig {
+  int32_t abi_version;      /* must be EVAC_ABI_VERSION */
+  int32_t seq_len;          /* S = number_of_pedestrians + 2 rows of the observation, 1 .. 64 */
+  int32_t d_model;          /* values per row: 6 (ohe), 3 (cat) or 2 (no statuses) */
+  int32_t num_heads;        /* RPOTransformerEmbeddingConfig.num_heads (3); 1 .. 4 */
+  int32_t dim_feedforward;  /* .dim_feedforward (96) */
+  int32_t num_blocks;       /* .num_blocks (2) */
+  int32_t use_resid;        /* .use_resid (0) */
+  float dropout;            /* .dropout (0.1); applied only when EvacPolicyIO.training != 0 */
+  float layer_norm_eps;     /* nn.LayerNorm default 1e-5 */
+  int32_t num_hidden;       /* RPOLinearNetworkConfig.num_hidden (64); multiple of 4, <= 64 */
+  int32_t action_dim;       /* 2; <= 3 */
+} EvacPolicyConfig;
+
+typedef struct EvacPolicy EvacPolicy;
+
+int evac_policy_default_config(EvacPolicyConfig* cfg, int32_t number_of_pedestrians, int32_t d_model);
+int evac_policy_create(const EvacPolicyConfig* cfg, int32_t device, EvacPolicy** out);
+int evac_policy_destroy(EvacPolicy* p);
+/* Number of floats evac_policy_load_weights expects, in this order (PyTorch parameter layouts, row-major):
+ *   for every block b: attention.Wq.weight [H*D, D], .bias [H*D], Wk.weight, Wk.bias, Wv.weight, Wv.bias,
+ *                      attention.dense.weight [D, H*D], .bias [D], ff.0.weight [F, D], ff.0.bias [F],
+ *                      ff.3.weight [D, F], ff.3.bias [D], norm1.weight [D], norm1.bias [D], norm2.weight [D], norm2.bias [D]
+ *   critic.0.weight [NH, S*D], .bias [NH], critic.2.weight [NH, NH], .bias [NH], critic.4.weight [1, NH], .bias [1],
+ *   actor_mean.0.weight [NH, S*D], .bias [NH], actor_mean.2.weight [NH, NH], .bias [NH], actor_mean.4.weight [A, NH], .bias [A],
+ *   actor_logstd [A] */
+int64_t evac_policy_num_weights(const EvacPolicy* p);
+/* `weights` is a HOST pointer; the library repacks it for the kernels and uploads it (synchronous). */
+int evac_policy_load_weights(EvacPolicy* p, const float* weights, int64_t count);
+/* Pre-allocate the internal embedding scratch for up to `max_envs` environments (needed before a forward call is
+ * captured in a CUDA graph without an `embedding` output buffer). */
+int evac_policy_reserve(EvacPolicy* p, int32_t max_envs);
+
+typedef struct EvacPolicyIO {
+  int32_t num_envs;
+  const float* obs;          /* [E, S*D] float32 (device) */
+  /* optional fused NormalizeObservation + clip: running mean / variance [E, S*D] updated in place with this step's
+   * observation (gymnasium RunningMeanStd, one sample per env and step), *norm_count = samples seen BEFORE this call
+   * (device double; the caller advances it), obs_norm (may be NULL) receives the normalised clipped observation */
+  float* norm_mean;
+  float* norm_var;
+  const double* norm_count;
+  float* obs_norm;
+  float norm_eps, norm_clip;
+  /* outputs (device), any may be NULL */
+  float* embedding;          /* [E, S*D] output of the transformer blocks */
+  float* mean;               /* [E, A] actor mean */
+  float* value;              /* [E] critic */
+  float* action;             /* [E, A] Normal(mean, exp(logstd)).sample() (or `given_action`, or the mean if !sample) */
+  float* action_clipped;     /* [E, A] clip(action, -1, 1) -- what evac_step consumes */
+  float* logprob;            /* [E] */
+  float* entropy;            /* [E] */
+  const float* given_action; /* optional [E, A]: evaluate the log-probability of this action instead of sampling */
+  int32_t sample;
+  int32_t training;          /* != 0: dropout active (the reference's rollouts never call .eval()) */
+  uint64_t seed, offset;     /* counter-based streams (dropout masks, Normal sampling): vary `offset` per call ... */
+  const uint64_t* offset_device; /* ... or point this at a DEVICE counter that is added to `offset` (NULL = unused): a
+                                    forward captured in a CUDA graph then draws fresh numbers on every replay */
+  int64_t env_index_offset;  /* global index of env 0 (sharding-invariant streams, like evac_create) */
+} EvacPolicyIO;
+
+/* embedding kernel (+ heads kernel if any head output is requested), asynchronous on `stream` */
+int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream);
+int64_t evac_policy_launch_count(const EvacPolicy* p);
+
+/* NormalizeReward(gamma) + clip for E environments (all pointers device, in place on returns / ret_mean / ret_var;
+ * *count = samples seen before this call). */
+int evac_normalize_reward(int32_t num_envs, const float* reward, const uint8_t* terminated, float* returns, float* ret_mean,
+                          float* ret_var, const double* count, float* out, float gamma, float eps, float clip, void* stream);
 
 /* ---- measurement helpers (used by bench.py; not part of the reference surface) ---- */
 /* FP32 FMA-pipe peak probe: every thread runs `iters` x 8 independent FMA chains; packed != 0 uses

@@ -8,7 +8,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libevac_b200.so")
+LIB_PATH = os.environ.get("EVAC_B200_LIB") or os.path.join(PKG_DIR, "libevac_b200.so")  # override: kernel-variant experiments
 SOURCES = [os.path.join(CSRC, "evac_abi.cu"), os.path.join(CSRC, "evac_policy.cu")]
 HEADERS = [os.path.join(CSRC, "evac_kernels.cuh"), os.path.join(CSRC, "evac_warp.cuh"), os.path.join(CSRC, "philox.cuh"),
            os.path.join(CSRC, "evac_policy.cuh"), os.path.join(os.path.dirname(PKG_DIR), "include", "evac_b200.h")]
@@ -38,7 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs, procs = [], []
     for src in SOURCES:  # one nvcc per translation unit, in parallel
         obj = os.path.join(CSRC, os.path.splitext(os.path.basename(src))[0] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas=-v"] if verbose else []), "-c", "-o", obj, src]
+        obj = obj[:-2] + os.environ.get("EVAC_B200_OBJ_TAG", "") + ".o"
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("EVAC_B200_NVCC_EXTRA", "").split(), *(["-Xptxas=-v"] if verbose else []), "-c", "-o", obj, src]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         objs.append(obj)

@@ -325,19 +325,60 @@ __device__ __forceinline__ void cell_list_pass(const Tile<float>& tile, const Ce
   constexpr int WARPS = THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.cells_x * a.cells_y;
-  // ---- 1. histogram
+  // ---- 1. histogram + rank of every source inside its cell.  The tile must come out sorted by (cell, pedestrian
+  // index) so that every float32 sum is deterministic.  Pedestrian index order = (pass k, warp, lane):
+  //   * lanes of one warp that share a cell find each other with MATCH.ANY (rank among them = lower lanes),
+  //   * the leader records the group size in cnt[warp][cell] (uint8; aliases the tile, which is only written in step 4)
+  //     and adds it to the cell counter (integer atomics commute),
+  //   * after the barrier a source's rank is counter-after-this-pass minus the groups of the warps at or above its own.
+  // If the [WARPS][C] byte table does not fit in the tile (more than 2048 cells at 32 warps) the ranks come from the
+  // arrival order of the atomics and are made canonical by counting lower indices in the cell (step 4b).
   for (int c = tid; c <= C; c += THREADS) cs.cell_start[c] = 0;
-  __syncthreads();
   int cell[PPT], rank[PPT];
   bool nan_src = false;
+  const bool fast_rank = (size_t)WARPS * C + 16 <= Tile<float>::bytes(THREADS * PPT);
+  if (fast_rank) {
+    uint8_t* cnt = reinterpret_cast<uint8_t*>(tile.P2);
+    const int n16 = (WARPS * C + 15) >> 4;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    cell[k] = 0; rank[k] = 0;
-    if (efv[k]) {
-      int cx, cy;
-      cell[k] = cell_of(px[k], py[k], a, cx, cy);
-      rank[k] = atomicAdd(&cs.cell_start[cell[k]], 1);
-      nan_src |= (ux[k] != ux[k]) | (uy[k] != uy[k]);
+    for (int k = 0; k < PPT; ++k) {
+      for (int i = tid; i < n16; i += THREADS) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
+      __syncthreads();
+      cell[k] = 0; rank[k] = 0;
+      int lrank = 0;
+      const uint32_t act = __ballot_sync(0xffffffffu, efv[k]);
+      if (efv[k]) {
+        int cx, cy;
+        cell[k] = cell_of(px[k], py[k], a, cx, cy);
+        nan_src |= (ux[k] != ux[k]) | (uy[k] != uy[k]);
+        const uint32_t peers = __match_any_sync(act, cell[k]);
+        lrank = __popc(peers & lt_mask);
+        if (lrank == 0) {
+          const int n = __popc(peers);
+          cnt[warp * C + cell[k]] = (uint8_t)n;
+          atomicAdd(&cs.cell_start[cell[k]], n);
+        }
+      }
+      __syncthreads();
+      if (efv[k]) {
+        int above = 0;
+        for (int w = warp; w < WARPS; ++w) above += cnt[w * C + cell[k]];
+        rank[k] = cs.cell_start[cell[k]] - above + lrank;
+      }
+      __syncthreads();  // cnt is cleared and the counters move on in the next pass
+    }
+  } else {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      cell[k] = 0; rank[k] = 0;
+      if (efv[k]) {
+        int cx, cy;
+        cell[k] = cell_of(px[k], py[k], a, cx, cy);
+        rank[k] = atomicAdd(&cs.cell_start[cell[k]], 1);
+        nan_src |= (ux[k] != ux[k]) | (uy[k] != uy[k]);
+      }
     }
   }
   // 0 * NaN = NaN: one source without a direction poisons EVERY sum in the reference (area.py:101,118)
@@ -359,19 +400,29 @@ __device__ __forceinline__ void cell_list_pass(const Tile<float>& tile, const Ce
   }
   __syncthreads();
   const int n_src = cs.cell_start[C];
-  // ---- 3. provisional scatter
+  // ---- 3. (arrival-order ranks only) provisional scatter, 4b. canonical rank = number of lower indices in the cell
+  if (!fast_rank) {
 #pragma unroll
-  for (int k = 0; k < PPT; ++k)
-    if (efv[k]) cs.list[cs.cell_start[cell[k]] + rank[k]] = (uint16_t)(k * THREADS + tid);
-  __syncthreads();
-  // ---- 4. canonical rank inside the cell + final scatter of the source records (tile / sorted_idx do not alias list)
+    for (int k = 0; k < PPT; ++k)
+      if (efv[k]) cs.list[cs.cell_start[cell[k]] + rank[k]] = (uint16_t)(k * THREADS + tid);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (efv[k]) {
+        const int i = k * THREADS + tid;
+        const int b = cs.cell_start[cell[k]], e = cs.cell_start[cell[k] + 1];
+        int r = 0;
+        for (int q = b; q < e; ++q) r += ((int)cs.list[q] < i);
+        rank[k] = r;
+      }
+    }
+  }
+  // ---- 4. final scatter of the source records (tile / sorted_idx do not alias list)
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
     if (efv[k]) {
       const int i = k * THREADS + tid;
-      const int b = cs.cell_start[cell[k]], e = cs.cell_start[cell[k] + 1];
-      int r = b;
-      for (int q = b; q < e; ++q) r += ((int)cs.list[q] < i);
+      const int r = cs.cell_start[cell[k]] + rank[k];
       const bool fv = (unsigned)(st[k] - ST_VISCEK) <= (unsigned)(ST_FOLLOWER - ST_VISCEK);
       tile.put(r, px[k], py[k], ux[k], uy[k]);
       cs.sorted_idx[r] = (uint16_t)(i | (fv ? 0x8000 : 0));

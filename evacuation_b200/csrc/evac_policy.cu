@@ -34,7 +34,7 @@ static int pfail(int code, const char* fmt, ...) {
 struct EvacPolicy {
   EvacPolicyConfig cfg;
   int device = 0;
-  int S = 0, D = 0, H = 0, F = 0, F4 = 0, NB = 0, NH = 0, A = 0, K = 0, K4 = 0;
+  int S = 0, D = 0, H = 0, F = 0, F4 = 0, NB = 0, NH = 0, A = 0, K = 0, K16 = 0;
   int wstride = 0;
   float* d_emb_w = nullptr;   // NB packed blocks
   float *d_w1t = nullptr, *d_b1 = nullptr, *d_w2t = nullptr, *d_b2 = nullptr, *d_w3 = nullptr, *d_b3 = nullptr, *d_logstd = nullptr;
@@ -150,17 +150,17 @@ int evac_policy_create(const EvacPolicyConfig* cfg, int32_t device, EvacPolicy**
   if (!p) return pfail(EVAC_ERR_INVALID, "out of host memory");
   p->cfg = *cfg; p->device = device;
   p->S = cfg->seq_len; p->D = cfg->d_model; p->H = cfg->num_heads; p->F = cfg->dim_feedforward; p->F4 = F4; p->NB = cfg->num_blocks;
-  p->NH = cfg->num_hidden; p->A = cfg->action_dim; p->K = p->S * p->D; p->K4 = round_up(p->K, 4);
+  p->NH = cfg->num_hidden; p->A = cfg->action_dim; p->K = p->S * p->D; p->K16 = round_up(p->K, HD_KC);
   p->wstride = ws;
   p->embed_smem = ((size_t)p->NB * ws + (size_t)PW_WARPS * 2 * p->H * PW_MAX_S) * sizeof(float);
-  p->heads_smem = ((size_t)HD_TM * (p->K4 + 4) + HD_TM * (HD_COLS + 4) + HD_TM * (HD_COLS + 1) + HD_TM * 4) * sizeof(float);
+  p->heads_smem = HD_SMEM_FLOATS * sizeof(float);
   if (p->embed_smem > 200 * 1024 || p->heads_smem > 200 * 1024) { delete p; return pfail(EVAC_ERR_UNSUPPORTED, "fused policy: shape needs too much shared memory"); }
   cudaError_t e = cudaSuccess;
   auto alloc = [&](float** q, size_t n) { if (e == cudaSuccess) { e = cudaMalloc(q, n * sizeof(float)); if (e == cudaSuccess) e = cudaMemset(*q, 0, n * sizeof(float)); } };
   alloc(&p->d_emb_w, (size_t)p->NB * ws);
-  alloc(&p->d_w1t, (size_t)p->K4 * HD_COLS); alloc(&p->d_b1, HD_COLS);
-  alloc(&p->d_w2t, (size_t)p->NH * HD_COLS); alloc(&p->d_b2, HD_COLS);
-  alloc(&p->d_w3, (size_t)(1 + p->A) * p->NH); alloc(&p->d_b3, 4); alloc(&p->d_logstd, 4);
+  alloc(&p->d_w1t, (size_t)p->K16 * HD_COLS); alloc(&p->d_b1, HD_COLS);
+  alloc(&p->d_w2t, (size_t)HD_HS * HD_COLS); alloc(&p->d_b2, HD_COLS);
+  alloc(&p->d_w3, (size_t)(1 + p->A) * HD_HS); alloc(&p->d_b3, 4); alloc(&p->d_logstd, 4);
   if (e != cudaSuccess) { evac_policy_destroy(p); return pfail(EVAC_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
   *out = p;
   return EVAC_OK;
@@ -202,15 +202,17 @@ int evac_policy_load_weights(EvacPolicy* p, const float* w, int64_t count) {
   const float* a2w = a0b + NH; const float* a2b = a2w + NH * NH;
   const float* a4w = a2b + NH; const float* a4b = a4w + A * NH;
   const float* lsd = a4b + A;
-  std::vector<float> w1t((size_t)p->K4 * HD_COLS, 0.f), b1(HD_COLS, 0.f), w2t((size_t)NH * HD_COLS, 0.f), b2(HD_COLS, 0.f), w3((size_t)(1 + A) * NH), b3(4, 0.f), ls(4, 0.f);
+  // heads: critic columns [0, 64), actor columns [64, 128), everything zero padded
+  std::vector<float> w1t((size_t)p->K16 * HD_COLS, 0.f), b1(HD_COLS, 0.f), w2t((size_t)HD_HS * HD_COLS, 0.f), b2(HD_COLS, 0.f),
+      w3((size_t)(1 + A) * HD_HS, 0.f), b3(4, 0.f), ls(4, 0.f);
   for (int o = 0; o < NH; ++o) {
-    for (int k = 0; k < K; ++k) { w1t[(size_t)k * HD_COLS + o] = c0w[(size_t)o * K + k]; w1t[(size_t)k * HD_COLS + NH + o] = a0w[(size_t)o * K + k]; }
-    b1[o] = c0b[o]; b1[NH + o] = a0b[o];
-    for (int k = 0; k < NH; ++k) { w2t[(size_t)k * HD_COLS + o] = c2w[o * NH + k]; w2t[(size_t)k * HD_COLS + NH + o] = a2w[o * NH + k]; }
-    b2[o] = c2b[o]; b2[NH + o] = a2b[o];
+    for (int k = 0; k < K; ++k) { w1t[(size_t)k * HD_COLS + o] = c0w[(size_t)o * K + k]; w1t[(size_t)k * HD_COLS + HD_HS + o] = a0w[(size_t)o * K + k]; }
+    b1[o] = c0b[o]; b1[HD_HS + o] = a0b[o];
+    for (int k = 0; k < NH; ++k) { w2t[(size_t)k * HD_COLS + o] = c2w[o * NH + k]; w2t[(size_t)k * HD_COLS + HD_HS + o] = a2w[o * NH + k]; }
+    b2[o] = c2b[o]; b2[HD_HS + o] = a2b[o];
   }
   for (int k = 0; k < NH; ++k) w3[k] = c4w[k];
-  for (int r = 0; r < A; ++r) for (int k = 0; k < NH; ++k) w3[(size_t)(1 + r) * NH + k] = a4w[r * NH + k];
+  for (int r = 0; r < A; ++r) for (int k = 0; k < NH; ++k) w3[(size_t)(1 + r) * HD_HS + k] = a4w[r * NH + k];
   b3[0] = c4b[0];
   for (int r = 0; r < A; ++r) { b3[1 + r] = a4b[r]; ls[r] = lsd[r]; }
   PCK(cudaDeviceSynchronize());
@@ -279,7 +281,7 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
   if (!heads) return EVAC_OK;
   HArgs h;
   memset(&h, 0, sizeof(h));
-  h.E = io->num_envs; h.K = p->K; h.K4 = p->K4; h.NH = p->NH; h.A = p->A;
+  h.E = io->num_envs; h.K = p->K; h.K16 = p->K16; h.NH = p->NH; h.A = p->A;
   h.emb = emb; h.w1t = p->d_w1t; h.b1 = p->d_b1; h.w2t = p->d_w2t; h.b2 = p->d_b2; h.w3 = p->d_w3; h.b3 = p->d_b3; h.logstd = p->d_logstd;
   h.given_action = io->given_action;
   h.mean = io->mean; h.value = io->value; h.action = io->action; h.action_clipped = io->action_clipped; h.logprob = io->logprob; h.entropy = io->entropy;

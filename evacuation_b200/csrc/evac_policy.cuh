@@ -31,7 +31,13 @@
 
 namespace evacp {
 
-constexpr int PW_WARPS = 4;   // environments (warps) per CTA of the embedding kernel
+#ifndef EVAC_PW_WARPS
+#define EVAC_PW_WARPS 4
+#endif
+#ifndef EVAC_PW_MINB
+#define EVAC_PW_MINB 4
+#endif
+constexpr int PW_WARPS = EVAC_PW_WARPS;   // environments (warps) per CTA of the embedding kernel
 constexpr int PW_MAX_S = 64;  // rows per environment handled by one warp
 
 __host__ __device__ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -195,7 +201,7 @@ __device__ __forceinline__ void attn_group(const float* __restrict__ ks, const f
 }
 
 template <int D, int H, bool TRAIN>
-__global__ void __launch_bounds__(PW_WARPS * 32, 4) evac_policy_embed_kernel(const __grid_constant__ PArgs a) {
+__global__ void __launch_bounds__(PW_WARPS * 32, EVAC_PW_MINB) evac_policy_embed_kernel(const __grid_constant__ PArgs a) {
   using L = EmbLayout<D, H>;
   extern __shared__ float4 smem4[];
   float* wsm = reinterpret_cast<float*>(smem4);
@@ -402,18 +408,31 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 4) evac_policy_embed_kernel(con
 
 // ------------------------------------------------------------------------------------------------------------------
 // critic / actor heads + sampling
+//
+// CTA = 2 warps = 32 environments x 128 hidden columns (columns [0, 64) critic, [64, 128) actor; a head narrower than 64
+// is zero-padded).  Layer 1 is a register-tiled [32 x K] x [K x 128] product: K in chunks of 16, the weight chunk
+// [16][128] and the embedding chunk [32][16] double-buffered in shared memory with cp.async, every thread an
+// 8-environment x 8-column tile (columns 4c..4c+3 of BOTH heads, so that the 16 lanes of a half-warp read one contiguous
+// 256-byte weight row segment; the two half-warps take different environments) = 64 accumulators, 256 FFMA per 16
+// LDS.128.  Layer 2 (two NH x NH products) reuses the tile shape with the weights staged once per CTA.
 constexpr int HD_TM = 32;        // environments per CTA
-constexpr int HD_THREADS = 256;  // 128 output columns x 2 environment halves
-constexpr int HD_COLS = 128;     // 2 * NH padded: [critic hidden | actor hidden]
+constexpr int HD_THREADS = 64;
+constexpr int HD_COLS = 128;     // [critic hidden (64) | actor hidden (64)]
+constexpr int HD_HS = 64;        // column stride between the two heads
+constexpr int HD_KC = 16;        // K chunk
+constexpr int HD_XS = HD_KC + 4; // padded row of the embedding chunk
+constexpr int HD_H1S = HD_COLS + 4;
+constexpr int HD_H2S = HD_COLS + 1;
+constexpr size_t HD_SMEM_FLOATS = 2 * HD_KC * HD_COLS + 2 * HD_TM * HD_XS + HD_HS * HD_COLS + HD_TM * HD_H1S + HD_TM * HD_H2S + HD_TM * 4;
 
 struct HArgs {
-  int E, K, K4, NH, A;           // K = S * D inputs, K4 = K rounded up to 4
+  int E, K, K16, NH, A;          // K = S * D inputs, K16 = K rounded up to the chunk
   const float* emb;              // [E, K]
-  const float* w1t;              // [K4, 128]  column o < NH: critic.0.weight[o], NH <= o < 2 NH: actor_mean.0.weight[o - NH]
+  const float* w1t;              // [K16, 128]  column o < 64: critic.0.weight[o], 64 <= o: actor_mean.0.weight[o - 64] (zero padded)
   const float* b1;               // [128]
-  const float* w2t;              // [NH, 128]  row k, column o: (critic|actor).2.weight[o % NH][k] of o's own head
+  const float* w2t;              // [64, 128]   row k, column o: (critic|actor).2.weight[o % 64][k] of o's own head (zero padded)
   const float* b2;               // [128]
-  const float* w3;               // [(1 + A), NH]: critic.4.weight, actor_mean.4.weight rows
+  const float* w3;               // [(1 + A), 64]: critic.4.weight, actor_mean.4.weight rows (zero padded)
   const float* b3;               // [1 + A]
   const float* logstd;           // [A]
   const float* given_action;     // optional [E, A]: evaluate this action instead of sampling (rpo_alpha perturbation excluded)
@@ -430,73 +449,151 @@ struct HArgs {
   long long env_offset;
 };
 
-__global__ void __launch_bounds__(HD_THREADS, 2) evac_policy_heads_kernel(const __grid_constant__ HArgs a) {
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// acc[i][c] += x[i] . w[c] over four consecutive k: x = 8 float4 (one per environment), w rows from shared memory
+__device__ __forceinline__ void heads_tile_fma(float (&acc)[8][8], const float4 (&x)[8], const float* __restrict__ wrow, int cq) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 wa = *reinterpret_cast<const float4*>(wrow + q * HD_COLS + 4 * cq);
+    const float4 wb = *reinterpret_cast<const float4*>(wrow + q * HD_COLS + HD_HS + 4 * cq);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xv = q == 0 ? x[i].x : q == 1 ? x[i].y : q == 2 ? x[i].z : x[i].w;
+      acc[i][0] = fmaf(xv, wa.x, acc[i][0]); acc[i][1] = fmaf(xv, wa.y, acc[i][1]);
+      acc[i][2] = fmaf(xv, wa.z, acc[i][2]); acc[i][3] = fmaf(xv, wa.w, acc[i][3]);
+      acc[i][4] = fmaf(xv, wb.x, acc[i][4]); acc[i][5] = fmaf(xv, wb.y, acc[i][5]);
+      acc[i][6] = fmaf(xv, wb.z, acc[i][6]); acc[i][7] = fmaf(xv, wb.w, acc[i][7]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(HD_THREADS) evac_policy_heads_kernel(const __grid_constant__ HArgs a) {
   extern __shared__ float4 smem4[];
-  float* xs = reinterpret_cast<float*>(smem4);   // [HD_TM][K4 + 4]
-  const int xstride = a.K4 + 4;
-  float* h1 = xs + HD_TM * xstride;              // [HD_TM][HD_COLS + 4]   (float4 reads along k)
-  float* h2 = h1 + HD_TM * (HD_COLS + 4);        // [HD_TM][HD_COLS + 1]   (scalar reads, env varies across lanes)
-  float* o3 = h2 + HD_TM * (HD_COLS + 1);        // [HD_TM][4]: value, mean...
-  const int tid = threadIdx.x, e0 = blockIdx.x * HD_TM;
+  float* wc = reinterpret_cast<float*>(smem4);        // [2][HD_KC][HD_COLS]
+  float* xc = wc + 2 * HD_KC * HD_COLS;               // [2][HD_TM][HD_XS]
+  float* w2s = xc + 2 * HD_TM * HD_XS;                // [HD_HS][HD_COLS]
+  float* h1 = w2s + HD_HS * HD_COLS;                  // [HD_TM][HD_H1S]   (float4 reads along k)
+  float* h2 = h1 + HD_TM * HD_H1S;                    // [HD_TM][HD_H2S]   (scalar reads, env varies across lanes)
+  float* o3 = h2 + HD_TM * HD_H2S;                    // [HD_TM][4]: value, mean...
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int e0 = blockIdx.x * HD_TM;
   const int ne = min(HD_TM, a.E - e0);
-  // ---- X tile: the 32 embeddings are one contiguous block of ne * K floats
-  for (int i = tid; i < HD_TM * xstride; i += HD_THREADS) {
-    const int r = i / xstride, k = i - r * xstride;
-    xs[i] = (r < ne && k < a.K) ? a.emb[(size_t)(e0 + r) * a.K + k] : 0.f;
+  const int cq = lane & 15;                            // column quad: columns 4cq..4cq+3 and 64+4cq..64+4cq+3
+  const int eb = warp * 16 + (lane >> 4) * 8;          // first of this thread's 8 environments
+  const bool x_vec = (a.K & 3) == 0;                   // rows of the embedding are 16-byte aligned
+
+  auto load_chunk = [&](int c, int buf) {
+    const int k0 = c * HD_KC;
+    float* wd = wc + buf * HD_KC * HD_COLS;
+    const float* ws = a.w1t + (size_t)k0 * HD_COLS;    // 16 x 128 floats, contiguous (rows >= K are zero)
+#pragma unroll
+    for (int i = 0; i < HD_KC * HD_COLS / 4 / HD_THREADS; ++i) {
+      const int v = i * HD_THREADS + tid;
+      cp_async16(wd + 4 * v, ws + 4 * v, 16);
+    }
+    float* xd = xc + buf * HD_TM * HD_XS;
+    if (x_vec) {
+#pragma unroll
+      for (int i = 0; i < HD_TM * HD_KC / 4 / HD_THREADS; ++i) {
+        const int v = i * HD_THREADS + tid, r = v >> 2, kq = (v & 3) * 4;
+        const int k = k0 + kq;
+        const int bytes = (r < ne && k < a.K) ? 16 : 0;   // K % 4 == 0: a float4 is entirely inside or outside the row
+        cp_async16(xd + r * HD_XS + kq, a.emb + (size_t)(e0 + min(r, ne - 1)) * a.K + min(k, a.K - 4), bytes);
+      }
+    } else {
+      for (int v = tid; v < HD_TM * HD_KC; v += HD_THREADS) {
+        const int r = v / HD_KC, kk = v - r * HD_KC, k = k0 + kk;
+        xd[r * HD_XS + kk] = (r < ne && k < a.K) ? a.emb[(size_t)(e0 + r) * a.K + k] : 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+
+  float acc[8][8];
+  // ---- layer 1
+  {
+    const float4 ba = *reinterpret_cast<const float4*>(a.b1 + 4 * cq), bb = *reinterpret_cast<const float4*>(a.b1 + HD_HS + 4 * cq);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i][0] = ba.x; acc[i][1] = ba.y; acc[i][2] = ba.z; acc[i][3] = ba.w;
+      acc[i][4] = bb.x; acc[i][5] = bb.y; acc[i][6] = bb.z; acc[i][7] = bb.w;
+    }
+    const int chunks = a.K16 / HD_KC;
+    load_chunk(0, 0);
+    // the layer-2 weights ride along as their own (oldest-but-one) group
+    for (int v = tid; v < HD_HS * HD_COLS / 4; v += HD_THREADS) cp_async16(w2s + 4 * v, a.w2t + 4 * v, 16);
+    cp_async_commit();
+    for (int c = 0; c < chunks; ++c) {
+      if (c + 1 < chunks) { load_chunk(c + 1, (c + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+      __syncthreads();
+      const float* wb_ = wc + (c & 1) * HD_KC * HD_COLS;
+      const float* xb_ = xc + (c & 1) * HD_TM * HD_XS + eb * HD_XS;
+#pragma unroll
+      for (int kk = 0; kk < HD_KC; kk += 4) {
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(xb_ + i * HD_XS + kk);
+        heads_tile_fma(acc, x, wb_ + kk * HD_COLS, cq);
+      }
+      __syncthreads();  // the buffer is refilled two iterations later
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      *reinterpret_cast<float4*>(h1 + (eb + i) * HD_H1S + 4 * cq) = make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+      *reinterpret_cast<float4*>(h1 + (eb + i) * HD_H1S + HD_HS + 4 * cq) = make_float4(tanhf(acc[i][4]), tanhf(acc[i][5]), tanhf(acc[i][6]), tanhf(acc[i][7]));
+    }
   }
   __syncthreads();
-  const int o = tid & (HD_COLS - 1), eh = (tid >> 7) * 16;
-  float acc[16];
-  // ---- layer 1: [16 envs] x [K] x [1 column] per thread
+  // ---- layer 2: columns 4cq.. of the critic read h1[.., 0:64), columns 64+4cq.. of the actor read h1[.., 64:128)
   {
-    const float b = a.b1[o];
+    const float4 ba = *reinterpret_cast<const float4*>(a.b2 + 4 * cq), bb = *reinterpret_cast<const float4*>(a.b2 + HD_HS + 4 * cq);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = b;
-    const float* __restrict__ wp = a.w1t + o;
-    const float* __restrict__ xp = xs + eh * xstride;
+    for (int i = 0; i < 8; ++i) {
+      acc[i][0] = ba.x; acc[i][1] = ba.y; acc[i][2] = ba.z; acc[i][3] = ba.w;
+      acc[i][4] = bb.x; acc[i][5] = bb.y; acc[i][6] = bb.z; acc[i][7] = bb.w;
+    }
 #pragma unroll 2
-    for (int k = 0; k < a.K4; k += 4) {
-      const float w0 = wp[(size_t)k * HD_COLS], w1 = wp[(size_t)(k + 1) * HD_COLS], w2 = wp[(size_t)(k + 2) * HD_COLS], w3 = wp[(size_t)(k + 3) * HD_COLS];
+    for (int k = 0; k < HD_HS; k += 4) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 x = *reinterpret_cast<const float4*>(xp + i * xstride + k);
-        acc[i] = fmaf(x.x, w0, acc[i]); acc[i] = fmaf(x.y, w1, acc[i]); acc[i] = fmaf(x.z, w2, acc[i]); acc[i] = fmaf(x.w, w3, acc[i]);
+      for (int q = 0; q < 4; ++q) {
+        const float4 wa = *reinterpret_cast<const float4*>(w2s + (k + q) * HD_COLS + 4 * cq);
+        const float4 wb = *reinterpret_cast<const float4*>(w2s + (k + q) * HD_COLS + HD_HS + 4 * cq);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xc_ = h1[(eb + i) * HD_H1S + k + q], xa_ = h1[(eb + i) * HD_H1S + HD_HS + k + q];
+          acc[i][0] = fmaf(xc_, wa.x, acc[i][0]); acc[i][1] = fmaf(xc_, wa.y, acc[i][1]);
+          acc[i][2] = fmaf(xc_, wa.z, acc[i][2]); acc[i][3] = fmaf(xc_, wa.w, acc[i][3]);
+          acc[i][4] = fmaf(xa_, wb.x, acc[i][4]); acc[i][5] = fmaf(xa_, wb.y, acc[i][5]);
+          acc[i][6] = fmaf(xa_, wb.z, acc[i][6]); acc[i][7] = fmaf(xa_, wb.w, acc[i][7]);
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) h1[(eh + i) * (HD_COLS + 4) + o] = tanhf(acc[i]);
-  }
-  __syncthreads();
-  // ---- layer 2: column o of its own head (critic: inputs h1[0, NH), actor: h1[NH, 2 NH))
-  {
-    const int NH = a.NH;
-    const int head_off = (o >= NH) ? NH : 0;
-    const float b = a.b2[o];
+    for (int i = 0; i < 8; ++i) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = b;
-    const float* __restrict__ wp = a.w2t + o;
-    const float* __restrict__ hp = h1 + eh * (HD_COLS + 4) + head_off;
-    for (int k = 0; k < NH; k += 4) {   // NH is a multiple of 4 (checked on the host)
-      const float w0 = wp[k * HD_COLS], w1 = wp[(k + 1) * HD_COLS], w2 = wp[(k + 2) * HD_COLS], w3 = wp[(k + 3) * HD_COLS];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 x = *reinterpret_cast<const float4*>(hp + i * (HD_COLS + 4) + k);
-        acc[i] = fmaf(x.x, w0, acc[i]); acc[i] = fmaf(x.y, w1, acc[i]); acc[i] = fmaf(x.z, w2, acc[i]); acc[i] = fmaf(x.w, w3, acc[i]);
+      for (int c = 0; c < 4; ++c) {
+        h2[(eb + i) * HD_H2S + 4 * cq + c] = tanhf(acc[i][c]);
+        h2[(eb + i) * HD_H2S + HD_HS + 4 * cq + c] = tanhf(acc[i][4 + c]);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) h2[(eh + i) * (HD_COLS + 1) + o] = tanhf(acc[i]);
   }
   __syncthreads();
   // ---- layer 3: value (row 0 of w3, critic hidden) and the action mean (rows 1..A, actor hidden)
   const int R = 1 + a.A;
   for (int t = tid; t < HD_TM * R; t += HD_THREADS) {
     const int r = t % R, el = t / R;
-    const float* __restrict__ hp = h2 + el * (HD_COLS + 1) + (r == 0 ? 0 : a.NH);
-    const float* __restrict__ w = a.w3 + r * a.NH;
+    const float* __restrict__ hp = h2 + el * HD_H2S + (r == 0 ? 0 : HD_HS);
+    const float* __restrict__ w = a.w3 + r * HD_HS;
     float s = a.b3[r];
     for (int k = 0; k < a.NH; ++k) s = fmaf(hp[k], w[k], s);
-    o3[el * 4 + (r < 4 ? r : 3)] = s;   // A <= 3 (checked on the host)
+    o3[el * 4 + r] = s;   // A <= 3 (checked on the host)
   }
   __syncthreads();
   // ---- Normal(mean, exp(logstd)): sample / log-probability / entropy [rpo_linear_agent_network.py:47-61]

@@ -22,7 +22,7 @@ POS = {"abs": 0, "rel": 1, "grav": 2}
 STAT = {"no": 0, "ohe": 1, "cat": 2}
 OBS = {"Dict": 0, "Box": 1}
 PREC = {"fp32": 0, "fp64": 1}
-AGENT = {"table": 0, "random": 1, "rotating": 2}
+AGENT = {"table": 0, "random": 1, "rotating": 2, "wacuum": 3}
 SEARCH = {"auto": 0, "brute": 1, "cells": 2}
 
 
@@ -83,7 +83,7 @@ SIGNATURES = {
     "evac_observe": (C.c_int, [_P, _P, _P]),
     "evac_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "evac_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
-    "evac_rollout": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "evac_rollout": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "evac_episode_stats": (C.c_int, [_P, _P, _P, _P, _P]),
     "evac_get_accumulators": (C.c_int, [_P, _P, _P, _P]),
     "evac_launch_count": (C.c_int64, [_P]),

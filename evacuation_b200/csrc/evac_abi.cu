@@ -57,6 +57,7 @@ struct EvacHandle {
   float* ep_stats = nullptr;
   uint8_t* ep_finished = nullptr;
   double* totals = nullptr;
+  int* agent_state = nullptr;
   // staging for the *_host entry points
   cudaStream_t stream = nullptr;
   float *h_actions = nullptr, *h_noise = nullptr, *h_obs = nullptr, *h_reward = nullptr;
@@ -124,6 +125,12 @@ static KArgs<real> make_args(const EvacHandle* h) {
   a.status = h->status; a.agent_pos = h->agent_pos; a.agent_dir = h->agent_dir;
   a.now = h->now; a.episode = h->episode; a.overall = h->overall; a.acc = h->acc;
   a.ep_stats = h->ep_stats; a.ep_finished = h->ep_finished; a.totals = h->totals;
+  a.agent_state = h->agent_state;
+  {  // baseline_wacuum_cleaner.py:17-28 (float64 expressions, compared against float32 positions -> rounded to float32)
+    const double half_reach = c.to_leader / 2.0;
+    a.wac_top = (float)(c.height - half_reach + c.step_size); a.wac_right = (float)(c.width - half_reach + c.step_size);
+    a.wac_left = (float)(-c.width + half_reach - c.step_size); a.wac_bottom = (float)(-c.height + half_reach - c.step_size);
+  }
   a.seed = h->seed; a.env_offset = h->env_offset;
   a.num_steps = 1; a.agent_kind = AGENT_TABLE;
   return a;
@@ -289,6 +296,7 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   ALLOC(h->overall, (size_t)h->E * sizeof(long long)); ALLOC(h->acc, (size_t)h->E * 3 * sizeof(double));
   ALLOC(h->ep_stats, (size_t)h->E * EVAC_NUM_EPISODE_STATS * sizeof(float)); ALLOC(h->ep_finished, (size_t)h->E);
   ALLOC(h->totals, (1 + EVAC_NUM_EPISODE_STATS) * sizeof(double));
+  ALLOC(h->agent_state, (size_t)h->E * sizeof(int));
 #undef ALLOC
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaDeviceSynchronize());
@@ -301,7 +309,7 @@ int evac_destroy(EvacHandle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   void* dptrs[] = {h->pos, h->dir, h->status, h->agent_pos, h->agent_dir, h->now, h->episode, h->overall, h->acc,
-                   h->ep_stats, h->ep_finished, h->totals, h->d_actions, h->d_noise, h->d_obs /* one block: obs | reward | flags */};
+                   h->ep_stats, h->ep_finished, h->totals, h->agent_state, h->d_actions, h->d_noise, h->d_obs /* one block: obs | reward | flags */};
   for (void* p : dptrs) if (p) cudaFree(p);
   void* hptrs[] = {h->h_actions, h->h_noise, h->h_obs /* one block */};
   for (void* p : hptrs) if (p) cudaFreeHost(p);
@@ -342,6 +350,7 @@ int evac_set_state(EvacHandle* h, const void* positions, const void* directions,
   if (agent_position) CK(cudaMemcpyAsync(h->agent_pos, agent_position, (size_t)h->E * 8, cudaMemcpyDeviceToDevice, st));
   if (agent_direction) CK(cudaMemcpyAsync(h->agent_dir, agent_direction, (size_t)h->E * 8, cudaMemcpyDeviceToDevice, st));
   if (now) CK(cudaMemcpyAsync(h->now, now, (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
+  if (agent_position) CK(cudaMemsetAsync(h->agent_state, 0, (size_t)h->E * sizeof(int), st));  // a moved agent restarts its script
   if (statuses) {
     CK(cudaMemcpyAsync(h->status, statuses, en, cudaMemcpyDeviceToDevice, st));
   } else if (positions || agent_position) {  // pedestrians.py:21-26: statuses follow from the positions
@@ -366,10 +375,11 @@ int evac_get_state(EvacHandle* h, void* positions, void* directions, uint8_t* st
 }
 
 int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const float* actions, const float* noise, float* obs,
-                 int32_t obs_every_step, float* reward_sum, uint8_t* terminated, uint8_t* truncated, void* stream) {
+                 int32_t obs_every_step, float* reward_sum, uint8_t* terminated, uint8_t* truncated, uint16_t* status_counts,
+                 void* stream) {
   if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
   if (num_steps < 1) return fail(EVAC_ERR_INVALID, "num_steps must be >= 1");
-  if (agent_kind < EVAC_AGENT_TABLE || agent_kind > EVAC_AGENT_ROTATING) return fail(EVAC_ERR_INVALID, "invalid agent_kind");
+  if (agent_kind < EVAC_AGENT_TABLE || agent_kind > EVAC_AGENT_WACUUM) return fail(EVAC_ERR_INVALID, "invalid agent_kind");
   if (agent_kind == EVAC_AGENT_TABLE && !actions) return fail(EVAC_ERR_INVALID, "actions is NULL");
   if (int r = set_device(h)) return r;
   cudaStream_t st = (cudaStream_t)stream;
@@ -377,18 +387,20 @@ int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const flo
     KArgs<double> a = make_args<double>(h);
     a.actions = (const float2*)actions; a.noise = noise; a.obs = obs; a.obs_every_step = obs_every_step;
     a.reward = reward_sum; a.terminated = terminated; a.truncated = truncated; a.num_steps = num_steps; a.agent_kind = agent_kind;
+    a.status_counts = status_counts;
     return launch_step<double>(h, a, st);
   }
   KArgs<float> a = make_args<float>(h);
   a.actions = (const float2*)actions; a.noise = noise; a.obs = obs; a.obs_every_step = obs_every_step;
   a.reward = reward_sum; a.terminated = terminated; a.truncated = truncated; a.num_steps = num_steps; a.agent_kind = agent_kind;
+  a.status_counts = status_counts;
   return launch_step<float>(h, a, st);
 }
 
 int evac_step(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward, uint8_t* terminated,
               uint8_t* truncated, void* stream) {
   if (!actions) return fail(EVAC_ERR_INVALID, "actions is NULL");
-  return evac_rollout(h, 1, EVAC_AGENT_TABLE, actions, noise, obs, 0, reward, terminated, truncated, stream);
+  return evac_rollout(h, 1, EVAC_AGENT_TABLE, actions, noise, obs, 0, reward, terminated, truncated, nullptr, stream);
 }
 
 static bool is_pinned(const void* p) {

@@ -37,7 +37,7 @@ constexpr int ST_NONE = 0, ST_VISCEK = 1, ST_FOLLOWER = 2, ST_EXITING = 3, ST_ES
 constexpr int POS_ABS = 0, POS_REL = 1, POS_GRAV = 2;
 constexpr int STAT_NO = 0, STAT_OHE = 1, STAT_CAT = 2;
 constexpr int OBS_DICT = 0, OBS_BOX = 1;
-constexpr int AGENT_TABLE = 0, AGENT_RANDOM = 1, AGENT_ROTATING = 2;
+constexpr int AGENT_TABLE = 0, AGENT_RANDOM = 1, AGENT_ROTATING = 2, AGENT_WACUUM = 3;
 constexpr int NUM_EPISODE_STATS = 9;
 constexpr float PARK = 1.0e18f;  // parking coordinate of non-moving slots: (1e18)^2*2 < FLT_MAX
 
@@ -81,6 +81,9 @@ struct KArgs {
   float* ep_stats;                 // [E,9] last finished episode
   uint8_t* ep_finished;            // [E]
   double* totals;                  // [1+9]
+  int* agent_state;                // [E]   WacuumCleaner state machine (phase | heading << 2 | steps-down << 8)
+  // WacuumCleaner lane edges [baseline_wacuum_cleaner.py:17-28], compared in float32 like NumPy's weak-scalar promotion
+  float wac_top, wac_right, wac_left, wac_bottom;
   // ---- per-call I/O
   const float2* actions;  // [steps,E] or NULL
   const float* noise;     // [steps,E,N] or NULL
@@ -89,6 +92,7 @@ struct KArgs {
   float* reward;          // [E]  (sum over steps)
   uint8_t* terminated;    // [E]  (OR over steps)
   uint8_t* truncated;     // [E]
+  uint16_t* status_counts;  // [steps,E,4] or NULL: escaped, exiting, following, viscek after every step (pedestrians.py:37-44)
   int num_steps, agent_kind;
   uint64_t seed;
   long long env_offset;
@@ -599,6 +603,29 @@ __device__ __forceinline__ void store_grav_obs(float* __restrict__ row, float ap
   row[5] = (float)gpy;
 }
 
+// WacuumCleaner.act [baseline_wacuum_cleaner.py:31-80]: climb to the top wall, sweep in horizontal lanes (25 steps down
+// between lanes), then walk to the exit.  state = phase (0 climb, 1 sweep, 2 exit) | heading-left << 2 | steps-down << 8.
+template <typename A>
+__device__ __forceinline__ void wacuum_act(float px, float py, int& state, const A& a, float& ax, float& ay) {
+  int phase = state & 3, left = (state >> 2) & 1, down = state >> 8;
+  ax = 0.f - px; ay = -1.f - py;  // task_2: exit_position - pos (float32)
+  if (phase == 0) {
+    if (py < a.wac_top) { ax = 0.f; ay = 1.f; }
+    else { phase = 1; ax = 1.f; ay = 0.f; }
+  } else if (phase == 1) {
+    if (down > 0) {
+      down -= 1;
+      if (py > a.wac_bottom) { ax = 0.f; ay = -1.f; }
+      else phase = 2;
+    } else {
+      const bool lane_open = left ? (px > a.wac_left) : (px < a.wac_right);
+      if (lane_open) { ax = left ? -1.f : 1.f; ay = 0.f; }
+      else { left ^= 1; down = 25; ax = 0.f; ay = -1.f; }
+    }
+  }
+  state = phase | (left << 2) | (down << 8);
+}
+
 // fresh random layout of one pedestrian [pedestrians.py:17-20]  // @region reset
 template <typename real>
 __device__ __forceinline__ void random_layout(uint64_t seed, uint32_t env, uint32_t episode, uint32_t ped, real& px,
@@ -656,6 +683,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       }
     }
     float2 ap = a.agent_pos[e], ad = a.agent_dir[e];
+    int wac_state = (a.agent_kind == AGENT_WACUUM) ? a.agent_state[e] : 0;
     int now = a.now[e];
     int episode = a.episode[e];
     const int now_start = now;
@@ -735,6 +763,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
           ax = av.x; ay = av.y;
         } else if (a.agent_kind == AGENT_RANDOM) {
           ax = action_r.x; ay = action_r.y;
+        } else if (a.agent_kind == AGENT_WACUUM) {
+          wacuum_act(ap.x, ap.y, wac_state, a, ax, ay);
         } else {  // RotatingAgent [rotating_agent.py:12-16]
           const float ph = 0.05f * (float)now;
           ax = sinf(ph); ay = cosf(ph);
@@ -838,6 +868,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         }
       }
       const int K_exit = q0 & 0xffff, K_fol = q0 >> 16, N_esc = q1 & 0xffff, N_exi = q1 >> 16, N_fol = q2;
+      if (a.status_counts != nullptr && tid == 0) {
+        const ushort4 c4 = make_ushort4((unsigned short)N_esc, (unsigned short)N_exi, (unsigned short)N_fol, (unsigned short)(N - N_esc - N_exi - N_fol));
+        reinterpret_cast<ushort4*>(a.status_counts)[(size_t)s * a.E + e] = c4;
+      }
       // ---------------- rewards + termination [reward.py:19-46, area.py:174-180, env.py:158-171]
       real tf, intrinsic;
       if constexpr (F64) { tf = (real)1 - (real)now / (real)(200 * N); intrinsic = (real)0 - (real)sd / (real)N; }
@@ -864,7 +898,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
           a.ep_finished[e] = 1;
         }
         acc_r = acc_i = acc_s = 0; acc_reset = true;
-        now = 0; episode += 1;
+        now = 0; episode += 1; wac_state = 0;
         ap = make_float2(0.f, 0.f); ad = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
@@ -923,6 +957,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
     if (tid == 0) {
       a.agent_pos[e] = ap; a.agent_dir[e] = ad;
       a.now[e] = now; a.episode[e] = episode; a.overall[e] += steps_total;
+      if (a.agent_kind == AGENT_WACUUM) a.agent_state[e] = wac_state;
       if (acc_reset) { a.acc[3 * (size_t)e] = acc_r; a.acc[3 * (size_t)e + 1] = acc_i; a.acc[3 * (size_t)e + 2] = acc_s; }
       else { a.acc[3 * (size_t)e] += acc_r; a.acc[3 * (size_t)e + 1] += acc_i; a.acc[3 * (size_t)e + 2] += acc_s; }
       if (a.reward) a.reward[e] = reward_sum;
@@ -963,6 +998,7 @@ __global__ void __launch_bounds__(128) evac_aux_kernel(const __grid_constant__ K
         a.status[(size_t)e * N + i] = (uint8_t)status_of<real>(px, py, (real)0, (real)0, a, d2e);
       }
       if (tid == 0) {
+        a.agent_state[e] = 0;
         a.agent_pos[e] = make_float2(0.f, 0.f); a.agent_dir[e] = make_float2(0.f, 0.f);
         a.now[e] = 0; a.episode[e] = episode;
         a.acc[3 * (size_t)e] = a.acc[3 * (size_t)e + 1] = a.acc[3 * (size_t)e + 2] = 0.0;

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
     }
   }
   float2 ap = a.agent_pos[e], ad = a.agent_dir[e];
+  int wac_state = (a.agent_kind == AGENT_WACUUM) ? a.agent_state[e] : 0;
   int now = a.now[e];
   int episode = a.episode[e];
   long long overall = 0;
@@ -193,6 +194,8 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
       } else if (a.agent_kind == AGENT_RANDOM) {  // RandomAgent: action_space.sample() ~ U[-1,1)^2 [random_agent.py:8-9]
         const uint2 r = evac_agent_block(a.seed, env_g, (uint32_t)episode, (uint32_t)now_prev);
         ax = 2.f * u01(r.x) - 1.f; ay = 2.f * u01(r.y) - 1.f;
+      } else if (a.agent_kind == AGENT_WACUUM) {
+        wacuum_act(ap.x, ap.y, wac_state, a, ax, ay);
       } else {  // RotatingAgent [rotating_agent.py:12-16]
         const float ph = 0.05f * (float)now;
         ax = sinf(ph); ay = cosf(ph);
@@ -262,6 +265,12 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
     counts = __reduce_add_sync(0xffffffffu, counts);
     const float sd = warp_sum(sum_dexit);
     const int K_exit = counts & 0xff, K_fol = (counts >> 8) & 0xff, N_esc = (counts >> 16) & 0xff, N_exi = (counts >> 24) & 0xff;
+    if (a.status_counts != nullptr) {  // pedestrians.status_stats after this step (before a same-step reset)
+      const int n_fol = __popc(__ballot_sync(0xffffffffu, q[0].st == ST_FOLLOWER)) + __popc(__ballot_sync(0xffffffffu, q[1].st == ST_FOLLOWER));
+      if (lane == 0)
+        reinterpret_cast<ushort4*>(a.status_counts)[(size_t)s * a.E + e] =
+            make_ushort4((unsigned short)N_esc, (unsigned short)N_exi, (unsigned short)n_fol, (unsigned short)(N - N_esc - N_exi - n_fol));
+    }
     const float tf = 1.f - (float)now * a.inv_200n, intrinsic = 0.f - sd * a.inv_n;
     float r_ped = a.init_reward;
     if (a.exit_reward) r_ped += (15.f + 10.f * tf) * (float)K_exit;
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
         a.ep_finished[e] = 1;
       }
       acc_r = acc_i = acc_s = 0;
-      now = 0; episode += 1;
+      now = 0; episode += 1; wac_state = 0;
       ap = make_float2(0.f, 0.f); ad = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -352,6 +361,7 @@ __global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant
   }
   if (lane == 0) {
     a.agent_pos[e] = ap; a.agent_dir[e] = ad;
+    if (a.agent_kind == AGENT_WACUUM) a.agent_state[e] = wac_state;
     a.now[e] = now; a.episode[e] = episode; a.overall[e] = overall;
     a.acc[3 * (size_t)e] = acc_r; a.acc[3 * (size_t)e + 1] = acc_i; a.acc[3 * (size_t)e + 2] = acc_s;
     if (a.reward) a.reward[e] = reward_sum;

@@ -505,12 +505,15 @@ class EvacuationEnv:
             return self._structure(obs[0]), float(rew[0]), bool(term[0]), bool(trunc[0]), {}
         return self._structure(obs), rew, term.astype(bool), trunc.astype(bool), {}
 
-    def rollout(self, num_steps: int, agent: str = "random", actions=None, noise=None, obs_every_step: bool = False):
+    def rollout(self, num_steps: int, agent: str = "random", actions=None, noise=None, obs_every_step: bool = False,
+                status_counts: bool = False):
         """`num_steps` consecutive steps in ONE kernel launch, state resident on chip.
 
-        agent: "random" (RandomAgent, random_agent.py:8-9), "rotating" (rotating_agent.py:12-16)
-        or "table" with actions [num_steps,E,2].  Returns (obs, reward_sum[E], terminated_any[E],
-        truncated_any[E]); obs is [E,...] after the last step or [num_steps,E,...]."""
+        agent: "random" (RandomAgent, random_agent.py:8-9), "rotating" (rotating_agent.py:12-16), "wacuum"
+        (WacuumCleaner, baseline_wacuum_cleaner.py:7-80, state machine on device) or "table" with actions
+        [num_steps,E,2].  Returns (obs, reward_sum[E], terminated_any[E], truncated_any[E]); obs is [E,...] after the
+        last step or [num_steps,E,...].  `status_counts=True` also records `pedestrians.status_stats` after every step
+        into `self.last_status_counts` ([num_steps,E,4] int16 tensor: escaped, exiting, following, viscek)."""
         h, lib = self._handle(), nat.load()
         E, N, dev = self.num_envs, self.cfg.number_of_pedestrians, self.device
         kind = nat.AGENT[agent]
@@ -522,10 +525,29 @@ class EvacuationEnv:
         obs = self._obs
         if obs_every_step:
             obs = torch.empty((num_steps, E, self.obs_dim), dtype=torch.float32, device=dev)
+        trace = torch.empty((num_steps, E, 4), dtype=torch.int16, device=dev) if status_counts else None
         nat.check(lib.evac_rollout(h, int(num_steps), kind, _ptr(act), _ptr(nz), _ptr(obs), int(obs_every_step),
-                                   _ptr(self._reward), _ptr(self._terminated), _ptr(self._truncated), self._stream()))
+                                   _ptr(self._reward), _ptr(self._terminated), _ptr(self._truncated), _ptr(trace), self._stream()))
         self._host_statuses = None
+        self.last_status_counts = trace
         return self._structure(obs), self._reward, self._terminated_b, self._truncated_b
+
+    def efficiency_curve(self, num_steps: int, agent: str = "random", chunk: int = 250):
+        """The "quantification of evacuation efficiency" statistic of src/plotting_old/plot.py:165-201: the number of
+        escaped pedestrians after every step, mean and standard deviation over the environments (one episode each,
+        from a fresh reset) -> (mean[num_steps], std[num_steps]) float64 tensors; `1 - mean / N` is the plotted
+        "% NOT evacuated".  Everything runs on the device (`evac_rollout` with the scripted `agent`); create the env
+        with auto_reset=False so that finished episodes stay at N escaped."""
+        self.reset()
+        means, stds = [], []
+        done = 0
+        while done < num_steps:
+            k = min(chunk, num_steps - done)
+            self.rollout(k, agent=agent, status_counts=True)
+            esc = self.last_status_counts[:, :, 0].to(torch.float64)
+            means.append(esc.mean(dim=1)); stds.append(esc.std(dim=1, unbiased=False))
+            done += k
+        return torch.cat(means), torch.cat(stds)
 
     def episode_statistics(self):
         """(stats [E,9] float32, finished [E] bool, totals [10] float64) -- per-env record of the last

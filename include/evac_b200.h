@@ -20,8 +20,11 @@
  *                                                                  src/env/wrappers/wrappers.py:8-96
  *                                GravityEncoding                   src/env/wrappers/gravity_encoding.py:41-81
  *   evac_rollout                 the caller's loop around step():  src/agents/rpo_agent.py:180-203 with
- *                                RandomAgent / RotatingAgent       src/agents/random_agent.py:8-9,
- *                                                                  src/agents/rotating_agent.py:12-16
+ *                                RandomAgent / RotatingAgent /     src/agents/random_agent.py:8-9,
+ *                                WacuumCleaner                     src/agents/rotating_agent.py:12-16,
+ *                                                                  src/agents/baseline_wacuum_cleaner.py:7-80
+ *                                + pedestrians.status_stats        src/env/env/pedestrians.py:37-44 (efficiency curve,
+ *                                                                  src/plotting_old/plot.py:165-201)
  *   evac_observe                 EvacuationEnv._get_observation + wrappers' observation()
  *                                                                  src/env/env/env.py:98-104
  *   evac_get_state/evac_set_state  env.unwrapped.{pedestrians,agent,time} attribute access
@@ -64,7 +67,7 @@ enum { EVAC_POS_ABS = 0, EVAC_POS_REL = 1, EVAC_POS_GRAV = 2 };     /* EnvWrappe
 enum { EVAC_STAT_NO = 0, EVAC_STAT_OHE = 1, EVAC_STAT_CAT = 2 };    /* EnvWrappersConfig.statuses  */
 enum { EVAC_OBS_DICT = 0, EVAC_OBS_BOX = 1 };                       /* EnvWrappersConfig.type      */
 enum { EVAC_PREC_F32 = 0, EVAC_PREC_F64 = 1 };                      /* pedestrian-state arithmetic */
-enum { EVAC_AGENT_TABLE = 0, EVAC_AGENT_RANDOM = 1, EVAC_AGENT_ROTATING = 2 }; /* evac_rollout action source */
+enum { EVAC_AGENT_TABLE = 0, EVAC_AGENT_RANDOM = 1, EVAC_AGENT_ROTATING = 2, EVAC_AGENT_WACUUM = 3 }; /* evac_rollout action source */
 /* neighbour search of the alignment pass (area.py:105-108 builds the full distance matrix):
  * AUTO = one-warp all-pairs tile for N <= 64, cell list (uniform grid, cell edge >= vision radius) above;
  * BRUTE = all-pairs shared-memory tiles for every N; CELLS = cell list whenever the shape supports it (N > 64, fp32) */
@@ -167,15 +170,19 @@ int evac_step_host(EvacHandle* h, const float* actions, const float* noise, floa
 
 /* `num_steps` consecutive steps in ONE kernel launch with the state kept on chip.
  *   agent_kind EVAC_AGENT_TABLE: actions [num_steps,E,2] float32; EVAC_AGENT_RANDOM: U[-1,1)^2
- *              from the Philox stream (RandomAgent); EVAC_AGENT_ROTATING: (sin, cos)(0.05 k)
+ *              from the Philox stream (RandomAgent); EVAC_AGENT_ROTATING: (sin, cos)(0.05 k);
+ *              EVAC_AGENT_WACUUM: the scripted sweep baseline (per-env state machine kept in the handle,
+ *              re-armed by a reset, a same-step auto-reset or evac_set_state(agent_position))
  *   noise      NULL or [num_steps,E,N] float32 (injected)
  *   obs        [E,obs_dim] (observation after the last step) or, if obs_every_step != 0,
  *              [num_steps,E,obs_dim]; NULL to skip
  *   reward_sum [E] float32: sum of the rewards of the num_steps steps (NULL to skip)
- *   terminated, truncated: [E] uint8, OR over the steps (NULL to skip) */
+ *   terminated, truncated: [E] uint8, OR over the steps (NULL to skip)
+ *   status_counts [num_steps,E,4] uint16 or NULL: escaped, exiting, following, viscek pedestrians after every step
+ *              (before a same-step auto-reset) -- the "escaped vs time" evacuation-efficiency statistic */
 int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const float* actions, const float* noise,
                  float* obs, int32_t obs_every_step, float* reward_sum, uint8_t* terminated, uint8_t* truncated,
-                 void* stream);
+                 uint16_t* status_counts, void* stream);
 
 /* Per-env statistics of the most recently FINISHED episode (auto_reset) -- [E, EVAC_NUM_EPISODE_STATS]
  * float32 plus finished[E] uint8 (1 if that env finished an episode since the last call; cleared by the call).

@@ -104,3 +104,40 @@ def test_wacuum_cleaner_matches_reference_trace(tag):
         gb = batched.act(torch.as_tensor(np.stack([pos, pos]))).numpy()
         np.testing.assert_allclose(gb[0], want, rtol=0, atol=1e-7)
         np.testing.assert_allclose(gb[1], want, rtol=0, atol=1e-7)
+
+
+def test_flat_weight_order_of_the_fused_policy_covers_the_reference_state_dict():
+    """`flatten_policy_weights` (the vector `evac_policy_load_weights` documents in include/evac_b200.h) consumes every
+    parameter of the reference module exactly once, in the documented order."""
+    from evacuation_b200.rollout import _FLAT_BLOCK_KEYS, _FLAT_HEAD_KEYS, flatten_policy_weights
+
+    z, x, net = _load_policy()
+    sd = {k[2:]: torch.as_tensor(z[k]) for k in z.files if k.startswith("w:")}   # names of the unmodified reference module
+    flat = flatten_policy_weights(sd, 2)
+    assert flat.dtype == torch.float32 and flat.numel() == sum(v.numel() for v in sd.values())
+    names = [f"embedding.{b}.{k}" for b in range(2) for k in _FLAT_BLOCK_KEYS] + list(_FLAT_HEAD_KEYS)
+    assert sorted(names) == sorted(sd.keys())
+    off = 0
+    for n in names:
+        v = sd[n].reshape(-1)
+        assert torch.equal(flat[off:off + v.numel()], v), n
+        off += v.numel()
+    # D = 6, H = 3, F = 96, NH = 64, A = 2: the count formula of evac_policy_num_weights
+    D, H, F, NH, A, K = 6, 3, 96, 64, 2, x.shape[1]
+    block = 3 * (H * D * D + H * D) + (D * H * D + D) + (F * D + F) + (D * F + D) + 4 * D
+    heads = 2 * (NH * K + NH + NH * NH + NH) + (NH + 1) + (A * NH + A) + A
+    assert flat.numel() == 2 * block + heads
+
+
+def test_fused_policy_fails_loudly_without_a_cuda_device():
+    """No CPU fallback: constructing the fused policy on a machine without a GPU raises."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from evacuation_b200._native import EvacNativeError
+    from evacuation_b200.rollout import FusedRPOTransformerPolicy
+
+    net = RPOTransformerPolicy(372, 60)
+    with pytest.raises(EvacNativeError):
+        FusedRPOTransformerPolicy(net, 60, device="cpu")
+    with pytest.raises((EvacNativeError, RuntimeError, AssertionError)):
+        FusedRPOTransformerPolicy(net, 60, device="cuda")

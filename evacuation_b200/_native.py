@@ -95,7 +95,7 @@ SIGNATURES = {
     "evac_policy_reserve": (C.c_int, [_P, C.c_int32]),
     "evac_policy_forward": (C.c_int, [_P, C.POINTER(EvacPolicyIO), _P]),
     "evac_policy_launch_count": (C.c_int64, [_P]),
-    "evac_normalize_reward": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P]),
+    "evac_normalize_reward": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P]),
     "evac_probe_fma": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "evac_probe_pairwise": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
 }

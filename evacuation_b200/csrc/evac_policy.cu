@@ -300,10 +300,11 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
 
 int64_t evac_policy_launch_count(const EvacPolicy* p) { return p ? p->launches : -1; }
 
-int evac_normalize_reward(int32_t num_envs, const float* reward, const uint8_t* terminated, float* returns, float* ret_mean,
-                          float* ret_var, const double* count, float* out, float gamma, float eps, float clip, void* stream) {
+int evac_normalize_reward(int32_t num_envs, const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns,
+                          float* ret_mean, float* ret_var, const double* count, float* out, float* done_out, float gamma, float eps,
+                          float clip, void* stream) {
   if (num_envs < 1 || !reward || !terminated || !returns || !ret_mean || !ret_var || !count || !out) return pfail(EVAC_ERR_INVALID, "evac_normalize_reward: NULL argument");
-  RArgs a{num_envs, reward, terminated, returns, ret_mean, ret_var, count, out, gamma, eps, clip};
+  RArgs a{num_envs, reward, terminated, truncated, done_out, returns, ret_mean, ret_var, count, out, gamma, eps, clip};
   evac_normalize_reward_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
   PCK(cudaGetLastError());
   return EVAC_OK;

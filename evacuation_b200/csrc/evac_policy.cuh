@@ -409,21 +409,26 @@ __global__ void __launch_bounds__(PW_WARPS * 32, EVAC_PW_MINB) evac_policy_embed
 // ------------------------------------------------------------------------------------------------------------------
 // critic / actor heads + sampling
 //
-// CTA = 2 warps = 32 environments x 128 hidden columns (columns [0, 64) critic, [64, 128) actor; a head narrower than 64
+// CTA = 32 environments x 128 hidden columns = one warp pair per split-K group (4 groups) (columns [0, 64) critic, [64, 128) actor; a head narrower than 64
 // is zero-padded).  Layer 1 is a register-tiled [32 x K] x [K x 128] product: K in chunks of 16, the weight chunk
 // [16][128] and the embedding chunk [32][16] double-buffered in shared memory with cp.async, every thread an
 // 8-environment x 8-column tile (columns 4c..4c+3 of BOTH heads, so that the 16 lanes of a half-warp read one contiguous
 // 256-byte weight row segment; the two half-warps take different environments) = 64 accumulators, 256 FFMA per 16
-// LDS.128.  Layer 2 (two NH x NH products) reuses the tile shape with the weights staged once per CTA.
+// LDS.128.  The K dimension is additionally split over HD_KS warp pairs (each takes one k-quad of every chunk; partial
+// tiles are summed through shared memory) so that 8192 environments put ~14 warps on every SM instead of ~3.5.
+// Layer 2 (two NH x NH products) reuses the tile shape and the split with the weights staged once per CTA.
 constexpr int HD_TM = 32;        // environments per CTA
-constexpr int HD_THREADS = 64;
+constexpr int HD_KS = 4;         // split-K groups: warp pair g accumulates the k with (k / 4) % 4 == g, then the groups are summed
+constexpr int HD_THREADS = 64 * HD_KS;
 constexpr int HD_COLS = 128;     // [critic hidden (64) | actor hidden (64)]
 constexpr int HD_HS = 64;        // column stride between the two heads
 constexpr int HD_KC = 16;        // K chunk
+static_assert(HD_KC == 4 * HD_KS, "one k-quad of every chunk per split-K group");
 constexpr int HD_XS = HD_KC + 4; // padded row of the embedding chunk
+constexpr int HD_STAGES = 4;     // cp.async ring: chunks are requested three iterations ahead (L2 latency >> one chunk of math)
 constexpr int HD_H1S = HD_COLS + 4;
 constexpr int HD_H2S = HD_COLS + 1;
-constexpr size_t HD_SMEM_FLOATS = 2 * HD_KC * HD_COLS + 2 * HD_TM * HD_XS + HD_HS * HD_COLS + HD_TM * HD_H1S + HD_TM * HD_H2S + HD_TM * 4;
+constexpr size_t HD_SMEM_FLOATS = HD_STAGES * HD_KC * HD_COLS + HD_STAGES * HD_TM * HD_XS + HD_HS * HD_COLS + HD_TM * HD_H1S + HD_TM * HD_H2S + HD_TM * 4;
 
 struct HArgs {
   int E, K, K16, NH, A;          // K = S * D inputs, K16 = K rounded up to the chunk
@@ -474,19 +479,42 @@ __device__ __forceinline__ void heads_tile_fma(float (&acc)[8][8], const float4 
   }
 }
 
-__global__ void __launch_bounds__(HD_THREADS) evac_policy_heads_kernel(const __grid_constant__ HArgs a) {
+__global__ void __launch_bounds__(HD_THREADS, 2) evac_policy_heads_kernel(const __grid_constant__ HArgs a) {
   extern __shared__ float4 smem4[];
-  float* wc = reinterpret_cast<float*>(smem4);        // [2][HD_KC][HD_COLS]
-  float* xc = wc + 2 * HD_KC * HD_COLS;               // [2][HD_TM][HD_XS]
-  float* w2s = xc + 2 * HD_TM * HD_XS;                // [HD_HS][HD_COLS]
+  float* wc = reinterpret_cast<float*>(smem4);        // [HD_STAGES][HD_KC][HD_COLS]
+  float* xc = wc + HD_STAGES * HD_KC * HD_COLS;       // [HD_STAGES][HD_TM][HD_XS]
+  float* w2s = xc + HD_STAGES * HD_TM * HD_XS;        // [HD_HS][HD_COLS]
   float* h1 = w2s + HD_HS * HD_COLS;                  // [HD_TM][HD_H1S]   (float4 reads along k)
   float* h2 = h1 + HD_TM * HD_H1S;                    // [HD_TM][HD_H2S]   (scalar reads, env varies across lanes)
   float* o3 = h2 + HD_TM * HD_H2S;                    // [HD_TM][4]: value, mean...
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kg = warp >> 1;                            // split-K group of this warp pair
+  const int t64 = tid & 63;                            // position inside the 64-thread tile grid
   const int e0 = blockIdx.x * HD_TM;
   const int ne = min(HD_TM, a.E - e0);
   const int cq = lane & 15;                            // column quad: columns 4cq..4cq+3 and 64+4cq..64+4cq+3
-  const int eb = warp * 16 + (lane >> 4) * 8;          // first of this thread's 8 environments
+  const int eb = (warp & 1) * 16 + (lane >> 4) * 8;    // first of this thread's 8 environments
+  float* red = wc;                                     // [64][65] split-K exchange, aliases the chunk buffers once they are drained
+  // sum the partial tiles of the split-K groups into group 0 (sequential rounds through one 16.6 KB buffer)
+  auto reduce_groups = [&](float (&t)[8][8]) {
+    __syncthreads();
+    for (int g = 1; g < HD_KS; ++g) {
+      if (kg == g) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) red[(i * 8 + c) * 65 + t64] = t[i][c];
+      }
+      __syncthreads();
+      if (kg == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) t[i][c] += red[(i * 8 + c) * 65 + t64];
+      }
+      __syncthreads();
+    }
+  };
   const bool x_vec = (a.K & 3) == 0;                   // rows of the embedding are 16-byte aligned
 
   auto load_chunk = [&](int c, int buf) {
@@ -500,9 +528,8 @@ __global__ void __launch_bounds__(HD_THREADS) evac_policy_heads_kernel(const __g
     }
     float* xd = xc + buf * HD_TM * HD_XS;
     if (x_vec) {
-#pragma unroll
-      for (int i = 0; i < HD_TM * HD_KC / 4 / HD_THREADS; ++i) {
-        const int v = i * HD_THREADS + tid, r = v >> 2, kq = (v & 3) * 4;
+      for (int v = tid; v < HD_TM * HD_KC / 4; v += HD_THREADS) {
+        const int r = v >> 2, kq = (v & 3) * 4;
         const int k = k0 + kq;
         const int bytes = (r < ne && k < a.K) ? 16 : 0;   // K % 4 == 0: a float4 is entirely inside or outside the row
         cp_async16(xd + r * HD_XS + kq, a.emb + (size_t)(e0 + min(r, ne - 1)) * a.K + min(k, a.K - 4), bytes);
@@ -519,48 +546,55 @@ __global__ void __launch_bounds__(HD_THREADS) evac_policy_heads_kernel(const __g
   float acc[8][8];
   // ---- layer 1
   {
-    const float4 ba = *reinterpret_cast<const float4*>(a.b1 + 4 * cq), bb = *reinterpret_cast<const float4*>(a.b1 + HD_HS + 4 * cq);
+    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+    if (kg == 0) { ba = *reinterpret_cast<const float4*>(a.b1 + 4 * cq); bb = *reinterpret_cast<const float4*>(a.b1 + HD_HS + 4 * cq); }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[i][0] = ba.x; acc[i][1] = ba.y; acc[i][2] = ba.z; acc[i][3] = ba.w;
       acc[i][4] = bb.x; acc[i][5] = bb.y; acc[i][6] = bb.z; acc[i][7] = bb.w;
     }
     const int chunks = a.K16 / HD_KC;
-    load_chunk(0, 0);
-    // the layer-2 weights ride along as their own (oldest-but-one) group
+    // the layer-2 weights ride along in the first group
     for (int v = tid; v < HD_HS * HD_COLS / 4; v += HD_THREADS) cp_async16(w2s + 4 * v, a.w2t + 4 * v, 16);
-    cp_async_commit();
-    for (int c = 0; c < chunks; ++c) {
-      if (c + 1 < chunks) { load_chunk(c + 1, (c + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-      __syncthreads();
-      const float* wb_ = wc + (c & 1) * HD_KC * HD_COLS;
-      const float* xb_ = xc + (c & 1) * HD_TM * HD_XS + eb * HD_XS;
 #pragma unroll
-      for (int kk = 0; kk < HD_KC; kk += 4) {
+    for (int c = 0; c < HD_STAGES - 1; ++c) {
+      if (c < chunks) load_chunk(c, c); else cp_async_commit();   // group index == chunk index, always
+    }
+    for (int c = 0; c < chunks; ++c) {
+      cp_async_wait<HD_STAGES - 2>();   // all but the newest HD_STAGES - 2 groups have landed -> chunk c is here
+      __syncthreads();                  // ... for every thread, and every warp is done with chunk c - 1, whose buffer is refilled now
+      if (c + HD_STAGES - 1 < chunks) load_chunk(c + HD_STAGES - 1, (c + HD_STAGES - 1) % HD_STAGES); else cp_async_commit();
+      const float* wb_ = wc + (c % HD_STAGES) * HD_KC * HD_COLS;
+      const float* xb_ = xc + (c % HD_STAGES) * HD_TM * HD_XS + eb * HD_XS;
+      {
+        const int kk = 4 * kg;  // HD_KC == 4 * HD_KS: one k-quad of every chunk per group
         float4 x[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(xb_ + i * HD_XS + kk);
         heads_tile_fma(acc, x, wb_ + kk * HD_COLS, cq);
       }
-      __syncthreads();  // the buffer is refilled two iterations later
     }
+    reduce_groups(acc);
+    if (kg == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      *reinterpret_cast<float4*>(h1 + (eb + i) * HD_H1S + 4 * cq) = make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
-      *reinterpret_cast<float4*>(h1 + (eb + i) * HD_H1S + HD_HS + 4 * cq) = make_float4(tanhf(acc[i][4]), tanhf(acc[i][5]), tanhf(acc[i][6]), tanhf(acc[i][7]));
+      for (int i = 0; i < 8; ++i) {
+        *reinterpret_cast<float4*>(h1 + (eb + i) * HD_H1S + 4 * cq) = make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+        *reinterpret_cast<float4*>(h1 + (eb + i) * HD_H1S + HD_HS + 4 * cq) = make_float4(tanhf(acc[i][4]), tanhf(acc[i][5]), tanhf(acc[i][6]), tanhf(acc[i][7]));
+      }
     }
   }
   __syncthreads();
   // ---- layer 2: columns 4cq.. of the critic read h1[.., 0:64), columns 64+4cq.. of the actor read h1[.., 64:128)
   {
-    const float4 ba = *reinterpret_cast<const float4*>(a.b2 + 4 * cq), bb = *reinterpret_cast<const float4*>(a.b2 + HD_HS + 4 * cq);
+    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+    if (kg == 0) { ba = *reinterpret_cast<const float4*>(a.b2 + 4 * cq); bb = *reinterpret_cast<const float4*>(a.b2 + HD_HS + 4 * cq); }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[i][0] = ba.x; acc[i][1] = ba.y; acc[i][2] = ba.z; acc[i][3] = ba.w;
       acc[i][4] = bb.x; acc[i][5] = bb.y; acc[i][6] = bb.z; acc[i][7] = bb.w;
     }
 #pragma unroll 2
-    for (int k = 0; k < HD_HS; k += 4) {
+    for (int k = kg * (HD_HS / HD_KS); k < (kg + 1) * (HD_HS / HD_KS); k += 4) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 wa = *reinterpret_cast<const float4*>(w2s + (k + q) * HD_COLS + 4 * cq);
@@ -575,12 +609,15 @@ __global__ void __launch_bounds__(HD_THREADS) evac_policy_heads_kernel(const __g
         }
       }
     }
+    reduce_groups(acc);
+    if (kg == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        h2[(eb + i) * HD_H2S + 4 * cq + c] = tanhf(acc[i][c]);
-        h2[(eb + i) * HD_H2S + HD_HS + 4 * cq + c] = tanhf(acc[i][4 + c]);
+        for (int c = 0; c < 4; ++c) {
+          h2[(eb + i) * HD_H2S + 4 * cq + c] = tanhf(acc[i][c]);
+          h2[(eb + i) * HD_H2S + HD_HS + 4 * cq + c] = tanhf(acc[i][4 + c]);
+        }
       }
     }
   }
@@ -639,6 +676,8 @@ struct RArgs {
   int E;
   const float* reward;
   const uint8_t* terminated;
+  const uint8_t* truncated;   // optional, with done_out
+  float* done_out;            // optional [E]: float(terminated | truncated) = next_done of rpo_agent.py:194
   float* returns;
   float* ret_mean;
   float* ret_var;
@@ -663,6 +702,7 @@ __global__ void evac_normalize_reward_kernel(const RArgs a) {
   a.ret_mean[e] = mean; a.ret_var[e] = var;
   const float z = __fmul_rn(r, rsqrtf(__fadd_rn(var, a.eps)));
   a.out[e] = min_nan(max_nan(z, -a.clip), a.clip);
+  if (a.done_out != nullptr) a.done_out[e] = (a.terminated[e] | (a.truncated ? a.truncated[e] : (uint8_t)0)) ? 1.f : 0.f;
 }
 
 }  // namespace evacp

@@ -327,17 +327,20 @@ class FusedRPOTransformerPolicy:
             pass
 
 
-def normalize_reward_fused(norm: "VectorNormalizer", reward: torch.Tensor, terminated: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """`VectorNormalizer.reward` as ONE kernel (evac_normalize_reward); `terminated` is the uint8/bool flag tensor of step()."""
+def normalize_reward_fused(norm: "VectorNormalizer", reward: torch.Tensor, terminated: torch.Tensor, out: torch.Tensor,
+                           truncated: Optional[torch.Tensor] = None, done_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`VectorNormalizer.reward` as ONE kernel (evac_normalize_reward); `terminated` / `truncated` are the uint8/bool flag
+    tensors of step().  With `truncated` and `done_out` the same pass writes next_done = float(terminated | truncated)."""
     import ctypes as C
 
     from . import _native as nat
 
     lib = nat.load()
-    term = terminated.view(torch.uint8) if terminated.dtype == torch.bool else terminated
+    u8 = lambda t: None if t is None else (t.view(torch.uint8) if t.dtype == torch.bool else t).data_ptr()
     st = torch.cuda.current_stream(reward.device).cuda_stream
-    nat.check(lib.evac_normalize_reward(reward.shape[0], reward.data_ptr(), term.data_ptr(), norm.returns.data_ptr(), norm.ret_mean.data_ptr(),
-                                        norm.ret_var.data_ptr(), norm.ret_count.data_ptr(), out.data_ptr(), norm.gamma, norm.epsilon,
+    nat.check(lib.evac_normalize_reward(reward.shape[0], reward.data_ptr(), u8(terminated), u8(truncated), norm.returns.data_ptr(),
+                                        norm.ret_mean.data_ptr(), norm.ret_var.data_ptr(), norm.ret_count.data_ptr(), out.data_ptr(),
+                                        None if done_out is None else done_out.data_ptr(), norm.gamma, norm.epsilon,
                                         norm.reward_clip, C.c_void_p(st)))
     norm.ret_count.add_(1.0)
     return out
@@ -383,8 +386,7 @@ class PolicyRollout:
                                 action_clipped=self._act_clipped, logprob=self.out["logprob"], value=self.out["value"])
             obs, reward, term, trunc, _ = self.env.step(self._act_clipped)
             assert obs.data_ptr() == self._raw_obs.data_ptr()
-            normalize_reward_fused(self.norm, reward, term, self.out["reward"])
-            self.next_done.copy_(torch.logical_or(term, trunc))
+            normalize_reward_fused(self.norm, reward, term, self.out["reward"], truncated=trunc, done_out=self.next_done)
             return
         action, logprob, _, value = self.policy.get_action_and_value(self.next_obs)
         obs, reward, term, trunc, _ = self.env.step(action.clamp(-1.0, 1.0).contiguous())  # ClipAction

@@ -278,9 +278,11 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream);
 int64_t evac_policy_launch_count(const EvacPolicy* p);
 
 /* NormalizeReward(gamma) + clip for E environments (all pointers device, in place on returns / ret_mean / ret_var;
- * *count = samples seen before this call). */
-int evac_normalize_reward(int32_t num_envs, const float* reward, const uint8_t* terminated, float* returns, float* ret_mean,
-                          float* ret_var, const double* count, float* out, float gamma, float eps, float clip, void* stream);
+ * *count = samples seen before this call).  Optionally (truncated, done_out non-NULL) also writes the rollout loop's
+ * next_done = float(terminated | truncated) (rpo_agent.py:194) in the same pass. */
+int evac_normalize_reward(int32_t num_envs, const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns,
+                          float* ret_mean, float* ret_var, const double* count, float* out, float* done_out, float gamma, float eps,
+                          float clip, void* stream);
 
 /* ---- measurement helpers (used by bench.py; not part of the reference surface) ---- */
 /* FP32 FMA-pipe peak probe: every thread runs `iters` x 8 independent FMA chains; packed != 0 uses

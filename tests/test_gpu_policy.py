@@ -148,7 +148,10 @@ def test_fused_normalizer_prologue_matches_vector_normalizer():
         rew = torch.randn(E, device="cuda", generator=g) * 3 - 1
         term = torch.rand(E, device="cuda", generator=g) < 0.2
         want_r = n_ref.reward(rew, term)
-        got_r = norm_reward(n_fused, rew, term, torch.empty(E, device="cuda"))
+        trunc = torch.rand(E, device="cuda", generator=g) < 0.1
+        done = torch.empty(E, device="cuda")
+        got_r = norm_reward(n_fused, rew, term, torch.empty(E, device="cuda"), truncated=trunc, done_out=done)
+        assert torch.equal(done, (term | trunc).float())
         np.testing.assert_allclose(got_r.cpu().numpy(), want_r.cpu().numpy(), rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(n_fused.returns.cpu().numpy(), n_ref.returns.cpu().numpy(), rtol=1e-6, atol=1e-7)
 

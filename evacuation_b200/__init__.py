@@ -9,8 +9,16 @@ from .wrappers import GravityEncoding, MatrixObs, PedestriansStatuses, RelativeP
 __all__ = [
     "setup_env", "EvacuationEnv", "Status", "SwitchDistances", "EnvConfig", "EnvWrappersConfig",
     "GravityEncoding", "PedestriansStatuses", "RelativePosition", "MatrixObs",
-    "BaseAgent", "RandomAgent", "RotatingAgent", "WacuumCleaner",
+    "BaseAgent", "RandomAgent", "RotatingAgent", "WacuumCleaner", "EvacuationVectorEnv",
 ]
+
+
+def __getattr__(name):  # lazy: vector.py pulls in torch-side glue (rollout.py)
+    if name == "EvacuationVectorEnv":
+        from .vector import EvacuationVectorEnv
+
+        return EvacuationVectorEnv
+    raise AttributeError(name)
 
 
 def setup_env(env_config: EnvConfig = None, wrap_config: EnvWrappersConfig = None, **batch_kwargs):

@@ -141,3 +141,14 @@ def test_fused_policy_fails_loudly_without_a_cuda_device():
         FusedRPOTransformerPolicy(net, 60, device="cpu")
     with pytest.raises((EvacNativeError, RuntimeError, AssertionError)):
         FusedRPOTransformerPolicy(net, 60, device="cuda")
+
+
+def test_vector_env_fails_loudly_without_a_cuda_device():
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    import evacuation_b200 as eb
+    from evacuation_b200._native import EvacNativeError
+
+    with pytest.raises((EvacNativeError, RuntimeError, AssertionError)):
+        eb.EvacuationVectorEnv(eb.EnvConfig(number_of_pedestrians=10), eb.EnvWrappersConfig(positions="rel", statuses="ohe", type="Box"),
+                               num_envs=4)

@@ -69,6 +69,7 @@ struct EvacHandle {
   int num_sms = 0;
   int cells_x = 0, cells_y = 0, cell_reach = 1;  // > 0: cell-list neighbour search (multi-warp fp32 shapes)
   bool warp_kernel = true;       // N <= 64 fp32: evac_warp_kernel (false: the generic kernel, EVAC_WARP_KERNEL=generic)
+  int warps_per_cta = 1;         // environments per CTA of evac_warp_kernel (EVAC_WARP_WPC = 1 | 2 | 4 | 8)
 };
 
 // smallest double b such that sqrt(v) >= t for every v >= b  <=>  (v < b) == (sqrt(v) < t)
@@ -167,10 +168,20 @@ static void pick_shape(int n, int* threads, int* ppt) {
 
 // N <= 64, float32: the dedicated one-warp kernel (evac_warp.cuh), observation encoding resolved at compile time.
 // EVAC_WARP_KERNEL=generic selects evac_step_kernel<float,32,2> instead (A/B measurements).
+template <int WPC>
+static void launch_warp_t(const KArgs<float>& a, cudaStream_t st) {
+  const int grid = (a.E + WPC - 1) / WPC;
+  if (a.positions == POS_REL && a.statuses == STAT_OHE && a.obs_type == OBS_BOX) evac_warp_kernel<WMODE_REL_OHE_BOX, WPC><<<grid, 32 * WPC, 0, st>>>(a);
+  else if (a.positions == POS_GRAV) evac_warp_kernel<WMODE_GRAV, WPC><<<grid, 32 * WPC, 0, st>>>(a);
+  else evac_warp_kernel<WMODE_GENERIC, WPC><<<grid, 32 * WPC, 0, st>>>(a);
+}
 static int launch_warp(EvacHandle* h, const KArgs<float>& a, cudaStream_t st) {
-  if (a.positions == POS_REL && a.statuses == STAT_OHE && a.obs_type == OBS_BOX) evac_warp_kernel<WMODE_REL_OHE_BOX><<<a.E, 32, 0, st>>>(a);
-  else if (a.positions == POS_GRAV) evac_warp_kernel<WMODE_GRAV><<<a.E, 32, 0, st>>>(a);
-  else evac_warp_kernel<WMODE_GENERIC><<<a.E, 32, 0, st>>>(a);
+  switch (h->warps_per_cta) {  // measured on B200 (tools/wpc_sweep.sh): 1 is the fastest at 4096 envs (14.0 / 14.4 / 14.4 / 14.9 us)
+    case 2: launch_warp_t<2>(a, st); break;
+    case 4: launch_warp_t<4>(a, st); break;
+    case 8: launch_warp_t<8>(a, st); break;
+    default: launch_warp_t<1>(a, st); break;
+  }
   CK(cudaGetLastError());
   h->launches++;
   return EVAC_OK;
@@ -264,6 +275,7 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   h->num_sms = prop.multiProcessorCount;
   pick_shape(h->N, &h->threads, &h->ppt);
   { const char* wk = getenv("EVAC_WARP_KERNEL"); h->warp_kernel = !(wk && strcmp(wk, "generic") == 0); }
+  { const char* wp = getenv("EVAC_WARP_WPC"); if (wp) h->warps_per_cta = atoi(wp); }
   if (h->N > 64 && h->threads > 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search != EVAC_SEARCH_BRUTE) {
     // cell edge >= (1 + 1e-4) x vision radius: two pedestrians closer than the radius always sit in the same or
     // in adjacent cells, float32 rounding of the cell index included; at most 64 x 64 cells

@@ -48,16 +48,21 @@ struct WPed {
   int st;       // status (ST_NONE for padding lanes)
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(32, 32) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
-  __shared__ __align__(16) float4 tile_s[66];  // Tile<float> of 64 slots (+ the look-ahead entries)
-  const Tile<float> tile(reinterpret_cast<unsigned char*>(tile_s), 64);
+// WPC = environments (independent warps) per CTA: fewer, fatter CTAs for the block scheduler; no block-level barrier anywhere.
+template <int MODE, int WPC>
+__global__ void __launch_bounds__(32 * WPC, 32 / WPC) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
+  __shared__ __align__(16) float4 tile_all[WPC][66];  // Tile<float> of 64 slots (+ the look-ahead entries) per warp
   // strip culling (a.cells_x > 0): the sources are sorted by vertical strip (edge >= vision radius) so that a
   // pedestrian only visits the slots of its own and the two adjacent strips
-  __shared__ uint2 strip_mask[32];   // per strip: which lanes' pedestrian 0 (.x) / pedestrian 1 (.y) sit in it
-  __shared__ int strip_start[33];    // first slot of every strip (+ total)
+  __shared__ uint2 strip_mask_all[WPC][32];   // per strip: which lanes' pedestrian 0 (.x) / pedestrian 1 (.y) sit in it
+  __shared__ int strip_start_all[WPC][33];    // first slot of every strip (+ total)
+  const int wic = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, e = blockIdx.x * WPC + wic, N = a.N;
+  if (e >= a.E) return;
+  const Tile<float> tile(reinterpret_cast<unsigned char*>(tile_all[wic]), 64);
+  uint2* strip_mask = strip_mask_all[wic];
+  int* strip_start = strip_start_all[wic];
   const int S = a.cells_x;
-  const int lane = threadIdx.x, e = blockIdx.x, N = a.N;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const bool valid[2] = {lane < N, lane + 32 < N};
   const uint32_t env_g = (uint32_t)(a.env_offset + e);

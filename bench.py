@@ -240,7 +240,8 @@ def run_ours(args):
     sampler.start()
     # head start for the host: the device spins ~30 ms while the first steps are enqueued, so that a host thread that is
     # briefly descheduled (N ranks + samplers share the box's cores) never leaves a gap INSIDE a per-step event pair
-    torch.cuda._sleep(int(0.03 * 1.9e9))
+    if not os.environ.get("EVAC_BENCH_NO_HEADSTART"):
+        torch.cuda._sleep(int(0.03 * 1.9e9))
     for s in range(K):
         flush.zero_()
         starts[s].record()

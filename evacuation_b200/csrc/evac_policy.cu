@@ -49,7 +49,7 @@ template <int D, int H>
 static int stride_of(int F4) { return EmbLayout<D, H>::stride(F4); }
 
 // (D, H) dispatch table
-#define EVAC_POLICY_SHAPES(X) X(6, 3) X(3, 3) X(2, 3) X(6, 1) X(6, 2) X(6, 4)
+#define EVAC_POLICY_SHAPES(X) X(6, 1) X(6, 2) X(6, 3) X(6, 4) X(3, 1) X(3, 2) X(3, 3) X(3, 4) X(2, 1) X(2, 2) X(2, 3) X(2, 4)
 
 static int block_stride(int D, int H, int F4) {
 #define X(d, h) if (D == d && H == h) return stride_of<d, h>(F4);

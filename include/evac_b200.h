@@ -216,7 +216,7 @@ typedef struct EvacPolicyConfig {
   int32_t abi_version;      /* must be EVAC_ABI_VERSION */
   int32_t seq_len;          /* S = number_of_pedestrians + 2 rows of the observation, 1 .. 64 */
   int32_t d_model;          /* values per row: 6 (ohe), 3 (cat) or 2 (no statuses) */
-  int32_t num_heads;        /* RPOTransformerEmbeddingConfig.num_heads (3); 1 .. 4 */
+  int32_t num_heads;        /* RPOTransformerEmbeddingConfig.num_heads (3); 1 .. 4 (every (d_model, num_heads) pair is instantiated) */
   int32_t dim_feedforward;  /* .dim_feedforward (96) */
   int32_t num_blocks;       /* .num_blocks (2) */
   int32_t use_resid;        /* .use_resid (0) */

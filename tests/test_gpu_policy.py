@@ -69,6 +69,30 @@ def test_fused_policy_matches_reference_network_golden():
     np.testing.assert_array_equal(o["action"].cpu().numpy(), z["sampled_action"])
 
 
+def test_fused_policy_matches_reference_network_variants():
+    """Hyper-parameter variants evaluated by the UNMODIFIED reference module (gen_policy_variants_golden.py): residual
+    blocks, 1 / 2 / 4 heads, d_model 3 / 2, 1 / 3 blocks, narrow feed-forward, 62 and 64 rows."""
+    Fused, _, Torch, _, _ = _mods()
+    z = np.load(os.path.join(HERE, "golden", "policy", "policy_variants.npz"))
+    for i in range(int(z["num_variants"])):
+        pre = f"v{i}:"
+        n, d, heads, dff, blocks, resid, nh = (int(v) for v in z[pre + "cfg"])
+        net = Torch((n + 2) * d, n, num_heads=heads, dim_feedforward=dff, num_blocks=blocks, use_resid=bool(resid), num_hidden=nh).eval()
+        net.load_state_dict({k[len(pre) + 2:]: torch.as_tensor(z[k]) for k in z.files if k.startswith(pre + "w:")}, strict=True)
+        fused = Fused(net, n, device="cuda").eval()
+        x = torch.as_tensor(z[pre + "x"]).cuda()
+        E = x.shape[0]
+        emb = torch.empty_like(x)
+        o = {k: torch.empty(s, device="cuda") for k, s in (("mean", (E, 2)), ("value", (E,)), ("logprob", (E,)))}
+        fused.forward(x, embedding=emb, given_action=torch.as_tensor(z[pre + "action"]).cuda(), **o)
+        torch.cuda.synchronize()
+        tol = 6e-5 if resid else 2e-5
+        np.testing.assert_allclose(emb.cpu().numpy(), z[pre + "embedding"], rtol=0, atol=tol, err_msg=f"variant {i}")
+        np.testing.assert_allclose(o["mean"].cpu().numpy(), z[pre + "actor_mean"], rtol=0, atol=tol, err_msg=f"variant {i}")
+        np.testing.assert_allclose(o["value"].cpu().numpy(), z[pre + "value"].reshape(-1), rtol=1e-5, atol=4 * tol, err_msg=f"variant {i}")
+        np.testing.assert_allclose(o["logprob"].cpu().numpy(), z[pre + "logprob"], rtol=1e-5, atol=1e-4, err_msg=f"variant {i}")
+
+
 @pytest.mark.parametrize("E", [1, 3, 70, 1000])
 def test_fused_policy_default_shape_vs_torch(E):
     net, fused = _make(60, 6, seed=E)

@@ -152,3 +152,32 @@ def test_vector_env_fails_loudly_without_a_cuda_device():
     with pytest.raises((EvacNativeError, RuntimeError, AssertionError)):
         eb.EvacuationVectorEnv(eb.EnvConfig(number_of_pedestrians=10), eb.EnvWrappersConfig(positions="rel", statuses="ohe", type="Box"),
                                num_envs=4)
+
+
+def _policy_variants():
+    z = np.load(os.path.join(HERE, "golden", "policy", "policy_variants.npz"))
+    for i in range(int(z["num_variants"])):
+        pre = f"v{i}:"
+        n, d, heads, dff, blocks, resid, nh = (int(v) for v in z[pre + "cfg"])
+        sd = {k[len(pre) + 2:]: torch.as_tensor(z[k]) for k in z.files if k.startswith(pre + "w:")}
+        kw = dict(num_heads=heads, dim_feedforward=dff, num_blocks=blocks, use_resid=bool(resid), num_hidden=nh)
+        yield i, n, d, kw, sd, {k: z[pre + k] for k in ("x", "embedding", "actor_mean", "value", "action", "logprob")}
+
+
+def test_policy_restatement_matches_reference_network_variants():
+    """Residual blocks, 1 / 2 / 4 heads, d_model 3 / 2, 1 / 3 blocks, narrow feed-forward, 62 and 64 rows: outputs of the
+    unmodified reference module (tests/golden/policy/gen_policy_variants_golden.py)."""
+    seen = 0
+    for i, n, d, kw, sd, g in _policy_variants():
+        net = RPOTransformerPolicy((n + 2) * d, n, **kw).eval()
+        missing, unexpected = net.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+        x = torch.as_tensor(g["x"])
+        with torch.no_grad():
+            emb = net.embed(x)
+            np.testing.assert_allclose(emb.numpy(), g["embedding"], rtol=1e-5, atol=2e-6, err_msg=f"variant {i}")
+            np.testing.assert_allclose(net.actor_mean(emb).numpy(), g["actor_mean"], rtol=1e-5, atol=2e-6)
+            np.testing.assert_allclose(net.get_value(x).numpy(), g["value"], rtol=1e-5, atol=2e-6)
+            _, lp, _, _ = net.get_action_and_value(x, torch.as_tensor(g["action"]))
+        seen += 1
+    assert seen == 6

@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(256) probe_fma_kernel(float* out, int iters, f
 
 // Standalone launch of the SAME pairwise_pass device function the fused step kernel uses, on the same
 // CTA shapes (one environment per CTA; THREADS x PPT = 32x2 or 64x1).
-template <int THREADS, int PPT>
+template <int THREADS, int PPT, int UNR = 4>
 __global__ void __launch_bounds__(THREADS) probe_pairwise_kernel(const float2* __restrict__ pos, const float2* __restrict__ unit,
                                                                  float2* __restrict__ out, int N, int reps, float thr2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(THREADS) probe_pairwise_kernel(const float2* _
   }
   __syncthreads();
   for (int r = 0; r < reps; ++r) {
-    pairwise_pass<PPT, false>(tile, N, xi, yi, thr2, sx, sy, cnt);
+    pairwise_pass<PPT, false, UNR>(tile, N, xi, yi, thr2, sx, sy, cnt);
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       accx[k] += sx[k]; accy[k] += sy[k];
@@ -557,6 +557,89 @@ __global__ void __launch_bounds__(THREADS) probe_pairwise_kernel(const float2* _
     const int i = k * THREADS + tid;
     if (i < N) out[(size_t)e * N + i] = make_float2(accx[k], accy[k]);
   }
+}
+
+// FMA-pipe micro-probes for the packed instruction mix of pairwise_pass (no shared memory, operands in registers):
+//   MODE 2: FFMA2 with three distinct 64-bit register operands per instruction (register-file bandwidth check)
+//   MODE 3: FADD2 with a scalar-broadcast operand, MODE 4: FMUL2, MODE 5: the pairwise mix (2 FADD2, FMUL2, FFMA2, 2 FSET, 2 FFMA2)
+template <int MODE>
+__global__ void __launch_bounds__(256) probe_mix_kernel(float* out, int iters, float seed_a, float seed_b) {
+  const float t = (float)threadIdx.x * 1e-3f;
+  float2 c[8], a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { c[k] = make_float2(t + k, t - k); a[k] = make_float2(seed_a + 1e-7f * k + 1e-9f * t, seed_a - 1e-7f * k - 1e-9f * t); b[k] = make_float2(seed_b * (k + 1) + 1e-9f * t, seed_b * (k + 2) - 1e-9f * t); }
+  if (MODE == 2) {
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = __ffma2_rn(c[k], a[k], b[k]);
+    }
+  } else if (MODE == 3) {
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = __fadd2_rn(c[k], make_float2(seed_b, seed_b));
+    }
+  } else if (MODE == 4) {
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = __fmul2_rn(c[k], a[k]);
+    }
+  } else if (MODE == 6) {  // FFMA2 acc = a(64-bit) * s(32-bit broadcast) + acc
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = __ffma2_rn(a[k], make_float2(b[k].x, b[k].x), c[k]);
+    }
+  } else if (MODE == 7) {  // FSETP + predicated FADD2 acc += a
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (b[k].x < c[k].y) c[k] = __fadd2_rn(c[k], a[k]);
+    }
+  } else if (MODE == 8) {  // FFMA2 acc = a * a + acc (two distinct 64-bit operands)
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = __ffma2_rn(a[k], a[k], c[k]);
+    }
+  } else if (MODE == 9) {  // FFMA2 acc = a0 * b + acc (a0 shared by consecutive instructions: operand-reuse cache)
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = __ffma2_rn(a[0], b[k], c[k]);
+    }
+  } else if (MODE == 10) {  // FFMA2 acc = a * b + acc, three distinct (accumulator form)
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = __ffma2_rn(a[k], b[k], c[k]);
+    }
+  } else if (MODE == 11) {  // scalar FFMA acc = a * b + acc, three distinct 32-bit operands (16 chains)
+    float* cs = reinterpret_cast<float*>(c); float* as = reinterpret_cast<float*>(a); float* bs = reinterpret_cast<float*>(b);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) cs[k] = fmaf(as[k], bs[k], cs[k]);
+    }
+  } else {
+    // sources: a[k] = (x_j, x_j+1), b[k] = (y_j, y_j+1), c[k] = (ux_j, ux_j+1); uy = a[k] again (values are irrelevant)
+    float2 nx[2] = {make_float2(-t, -t), make_float2(-t - 0.5f, -t - 0.5f)}, ny[2] = {make_float2(t, t), make_float2(t + 0.25f, t + 0.25f)};
+    float2 ax[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, ay[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float2 dx = __fadd2_rn(a[k], nx[q]);
+          const float2 dy = __fadd2_rn(b[k], ny[q]);
+          float2 d2 = __fmul2_rn(dx, dx);
+          d2 = __ffma2_rn(dy, dy, d2);
+          const float2 w = make_float2(d2.x < seed_a ? 1.f : 0.f, d2.y < seed_a ? 1.f : 0.f);
+          ax[q] = __ffma2_rn(w, c[k], ax[q]);
+          ay[q] = __ffma2_rn(w, a[k], ay[q]);
+        }
+      }
+      nx[0].x += 1e-9f * ax[0].x; nx[1].y += 1e-9f * ay[1].y;  // data dependence between iterations
+    }
+    c[0] = __fadd2_rn(__fadd2_rn(ax[0], ax[1]), __fadd2_rn(ay[0], ay[1]));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += c[k].x + c[k].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 extern "C" {
@@ -573,13 +656,27 @@ int evac_probe_fma(int32_t device, int32_t packed, int32_t iters, float* ms, dou
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   for (int rep = 0; rep < 2; ++rep) {
     CK(cudaEventRecord(e0));
-    if (packed) probe_fma_kernel<true><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f);
-    else probe_fma_kernel<false><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f);
+    switch (packed) {  // 0 scalar FFMA, 1 FFMA2 (shared operands); 2-5: probe_mix_kernel modes
+      case 0: probe_fma_kernel<false><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+      case 1: probe_fma_kernel<true><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+      case 2: probe_mix_kernel<2><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+      case 3: probe_mix_kernel<3><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+      case 4: probe_mix_kernel<4><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+      case 6: probe_mix_kernel<6><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+      case 7: probe_mix_kernel<7><<<blocks, threads>>>(out, iters, 1e-9f, 1e-7f); break;
+      case 8: probe_mix_kernel<8><<<blocks, threads>>>(out, iters, 1e-9f, 1e-7f); break;
+      case 9: probe_mix_kernel<9><<<blocks, threads>>>(out, iters, 1e-9f, 1e-7f); break;
+      case 10: probe_mix_kernel<10><<<blocks, threads>>>(out, iters, 1e-9f, 1e-7f); break;
+      case 11: probe_mix_kernel<11><<<blocks, threads>>>(out, iters, 1e-9f, 1e-7f); break;
+      default: probe_mix_kernel<5><<<blocks, threads>>>(out, iters, 0.5f, 1e-7f); break;
+    }
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
   }
   CK(cudaEventElapsedTime(ms, e0, e1));
-  *flops = (double)blocks * threads * (double)iters * 16.0 * 2.0;
+  // FMA-pipe lane-operations x 2 (an FFMA counts 2 flops; FADD2 / FMUL2 lane-ops are counted the same way so that every mode
+  // reads as FMA-pipe occupancy); mode 5 issues 96 packed FMA-pipe instructions (+ 32 FSET on the ALU pipe) per iteration
+  *flops = (double)blocks * threads * (double)iters * (packed == 5 ? 96.0 * 2.0 : 16.0) * 2.0;
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
   return EVAC_OK;
 }
@@ -606,9 +703,13 @@ int evac_probe_pairwise(int32_t device, int32_t num_envs, int32_t n, int32_t rep
   const float thr2 = round_up_f32(sq_boundary(0.1));
   const char* shape = getenv("EVAC_SHAPE_64");
   const bool shape_32x2 = !(shape && strcmp(shape, "64x1") == 0);
+  const char* unr_s = getenv("EVAC_PROBE_UNROLL");  // A/B: unroll factor of the slot-pair loop (2 | 4 | 8)
+  const int unr = unr_s ? atoi(unr_s) : 4;
   for (int rep = 0; rep < 2; ++rep) {
     CK(cudaEventRecord(e0));
-    if (shape_32x2) probe_pairwise_kernel<32, 2><<<num_envs, 32, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
+    if (shape_32x2 && unr == 8) probe_pairwise_kernel<32, 2, 8><<<num_envs, 32, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
+    else if (shape_32x2 && unr == 2) probe_pairwise_kernel<32, 2, 2><<<num_envs, 32, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
+    else if (shape_32x2) probe_pairwise_kernel<32, 2><<<num_envs, 32, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
     else probe_pairwise_kernel<64, 1><<<num_envs, 64, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));

@@ -219,7 +219,7 @@ struct Tile<double> {
 // The pairwise neighbour-alignment pass [area.py:105-119]: for each of this thread's PPT pedestrians
 // i, sum the unit directions of all slots j with |p_i - p_j|^2 < thr2 (self included).
 // count[] (number of neighbours, area.py:108) is only produced when COUNT is set (fp64 parity mode).
-template <int PPT, bool COUNT>  // @region pairwise
+template <int PPT, bool COUNT, int UNR = 4>  // @region pairwise
 __device__ __forceinline__ void pairwise_pass(const Tile<float>& t, int nslots, const float (&xi)[PPT],
                                               const float (&yi)[PPT], float thr2, float (&sx)[PPT], float (&sy)[PPT],
                                               float (&cnt)[PPT]) {
@@ -237,7 +237,7 @@ __device__ __forceinline__ void pairwise_pass(const Tile<float>& t, int nslots, 
   // computed, so the ~30-cycle shared-memory latency is off the dependent chain.  The tile carries one
   // spare entry per array, so the look-ahead load of the last iteration stays inside the allocation.
   float4 p = t.P2[0], u = t.U2[0];
-#pragma unroll 4
+#pragma unroll(UNR)
   for (int j = 0; j < n2; ++j) {
     const float4 pn = t.P2[j + 1];
     const float4 un = t.U2[j + 1];

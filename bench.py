@@ -213,6 +213,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner / warnings go to stderr: stdout = the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -341,6 +342,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    per_rank_us = [1e3 * kernel_ms / K]
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(t, torch.tensor([1e3 * kernel_ms / K], dtype=torch.float64, device=dev))
+        per_rank_us = [float(x) for x in t.tolist()]
     kernel_ms, flushed_ms, resident_ms, rollout_ms, e2e_s = maxr(kernel_ms), maxr(flushed_ms), maxr(resident_ms), maxr(rollout_ms), maxr(e2e_s)
     totals = allgather_episode_totals(u)  # the only collective: finished-episode statistics
 
@@ -385,6 +391,7 @@ def run_ours(args):
                     "api": "setup_env(..., batched=False).step(numpy actions) -> numpy obs, reward, flags (evac_step_host)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "us_per_step_by_rank": per_rank_us,
             "episodes_finished_all_ranks": float(totals[:, 0].sum()),
         }
         if world == 1 and not args.no_extra:
@@ -474,6 +481,7 @@ def run_c5(args):
     world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

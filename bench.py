@@ -201,6 +201,15 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def _nccl_output_to_stderr():
+    """stdout must stay the ONE JSON line.  With NCCL_DEBUG=VERSION (set on the GPU boxes) NCCL prints its version
+    banner on stdout and ignores NCCL_DEBUG_FILE (debug.cc: the file is only opened above VERSION), so raise the level
+    to WARN and send NCCL's output to stderr.  An explicit INFO / TRACE request is kept."""
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -213,7 +222,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner / warnings go to stderr: stdout = the one JSON line
+        _nccl_output_to_stderr()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -481,7 +490,7 @@ def run_c5(args):
     world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        _nccl_output_to_stderr()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

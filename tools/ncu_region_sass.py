@@ -1,11 +1,12 @@
 """List the SASS of one region (see tools/ncu_regions.py) with executed counts per warp.
-Usage: ncu -i X.ncu-rep --page source --csv --print-source cuda,sass | python tools/ncu_region_sass.py <region> <warps>"""
+Usage: ncu -i X.ncu-rep --page source --csv --print-source cuda,sass | python tools/ncu_region_sass.py <region> <warps> [kernel-substring]"""
 import csv
 import re
 import sys
 
 rows = list(csv.reader(sys.stdin))
 region, warps = sys.argv[1], float(sys.argv[2])
+want = sys.argv[3] if len(sys.argv) > 3 else None
 OWN = ("evac_kernels.cuh", "evac_warp.cuh")
 marks = {f: [(i + 1, m.group(1)) for i, l in enumerate(open("evacuation_b200/csrc/" + f).read().splitlines())
              for m in [re.search(r"@region\s+(\S+)", l)] if m] for f in OWN}
@@ -35,7 +36,7 @@ for r in rows:
         cur_file = r[1].split("/")[-1]
         continue
     if r[0] == "Function Name":
-        if first_fn is None:
+        if first_fn is None and (want is None or want in r[1]):
             first_fn = r[1]
         skip = r[1] != first_fn
         continue

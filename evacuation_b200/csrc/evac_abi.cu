@@ -61,6 +61,8 @@ struct EvacHandle {
   // staging for the *_host entry points
   cudaStream_t stream = nullptr;
   float *h_actions = nullptr, *h_noise = nullptr, *h_obs = nullptr, *h_reward = nullptr;
+  const void* pin_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // evac_step_host: caller pointers of the last call ...
+  bool pin_val[6] = {false, false, false, false, false, false};                      // ... and whether each was page-locked
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   float *d_actions = nullptr, *d_noise = nullptr, *d_obs = nullptr, *d_reward = nullptr;
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
@@ -441,8 +443,11 @@ int evac_step_host(EvacHandle* h, const float* actions, const float* noise, floa
   cudaStream_t st = h->stream;
   // Page-locked caller buffers are used directly (zero staging copies); pageable ones go through the
   // handle's pinned staging buffers.
-  const bool pa = is_pinned(actions), pn = is_pinned(noise), po = is_pinned(obs), pr = is_pinned(reward),
-             pt = is_pinned(terminated), pu = is_pinned(truncated);
+  // (a caller that re-uses its buffers -- the Python host face does -- pays the six attribute queries once)
+  const void* ptrs[6] = {actions, noise, obs, reward, terminated, truncated};
+  for (int i = 0; i < 6; ++i)
+    if (ptrs[i] != h->pin_key[i]) { h->pin_key[i] = ptrs[i]; h->pin_val[i] = is_pinned(ptrs[i]); }
+  const bool pa = h->pin_val[0], pn = h->pin_val[1], po = h->pin_val[2], pr = h->pin_val[3], pt = h->pin_val[4], pu = h->pin_val[5];
   if (!pa) memcpy(h->h_actions, actions, E * 8);
   CK(cudaMemcpyAsync(h->d_actions, pa ? actions : h->h_actions, E * 8, cudaMemcpyHostToDevice, st));
   if (noise) {

@@ -471,26 +471,31 @@ class EvacuationEnv:
                 self.agent.save()
             return (self._obs_view, self._reward, self._terminated_b, self._truncated_b, {})
         # ---- single-env face: host buffers through evac_step_host
-        act = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(E, 2))
         if noise is None and self.rng == "numpy":
             noise = self._numpy_noise()
         nz = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float32).reshape(E, N))
         if self._host is None:
-            # ONE page-locked block [obs | reward | terminated | truncated]: evac_step_host fills it with a single D2H copy
+            # ONE page-locked block [obs | reward | terminated | truncated]: evac_step_host fills it with a single D2H copy;
+            # the actions are staged in a page-locked array too, so the library copies straight from it.  Pointers are
+            # taken once (ctypes / data_ptr conversions are a measurable part of a 150 us step).
             D = self.obs_dim
             blk = torch.empty(E * D * 4 + E * 4 + 2 * E, dtype=torch.uint8, pin_memory=True)
             o0, r0, t0 = E * D * 4, E * D * 4 + E * 4, E * D * 4 + E * 4 + E
             self._host_block = blk
             self._host = dict(obs=blk[:o0].view(torch.float32).view(E, D), rew=blk[o0:r0].view(torch.float32), term=blk[r0:t0], trunc=blk[t0:])
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
-        hb = self._host
+            self._host_np["term_b"], self._host_np["trunc_b"] = self._host_np["term"].view(np.bool_), self._host_np["trunc"].view(np.bool_)
+            self._act_pin = torch.empty((E, 2), dtype=torch.float32, pin_memory=True)
+            self._act_np = self._act_pin.numpy()
+            self._host_ptrs = tuple(_ptr(t) for t in (self._act_pin, self._host["obs"], self._host["rew"], self._host["term"], self._host["trunc"]))
+        self._act_np[...] = np.asarray(action, dtype=np.float32).reshape(E, 2)
         # outputs alias the page-locked buffers and are valid until the next step (the reference's
         # observations alias live state in the same way, env.py:100-102)
-        obs, rew, term, trunc = (self._host_np[k] for k in ("obs", "rew", "term", "trunc"))
+        hn = self._host_np
+        obs, rew, term, trunc = hn["obs"], hn["rew"], hn["term"], hn["trunc"]
         torch.cuda.current_stream(self.device).synchronize()
-        nat.check(lib.evac_step_host(h, act.ctypes.data_as(C.c_void_p),
-                                     None if nz is None else nz.ctypes.data_as(C.c_void_p),
-                                     _ptr(hb["obs"]), _ptr(hb["rew"]), _ptr(hb["term"]), _ptr(hb["trunc"])))
+        pa, po, pr, pt, pu = self._host_ptrs
+        nat.check(lib.evac_step_host(h, pa, None if nz is None else nz.ctypes.data_as(C.c_void_p), po, pr, pt, pu))
         if self.rng == "numpy":
             self._host_statuses = self.get_state()["statuses"].cpu().numpy()
         if self.draw:
@@ -503,7 +508,7 @@ class EvacuationEnv:
                     log.warning("animation skipped: %s", exc)
         if E == 1:
             return self._structure(obs[0]), float(rew[0]), bool(term[0]), bool(trunc[0]), {}
-        return self._structure(obs), rew, term.astype(bool), trunc.astype(bool), {}
+        return self._structure(obs), rew, hn["term_b"], hn["trunc_b"], {}
 
     def rollout(self, num_steps: int, agent: str = "random", actions=None, noise=None, obs_every_step: bool = False,
                 status_counts: bool = False):

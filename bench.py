@@ -119,11 +119,12 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # CPU side: the oracle port of the reference's per-env step loop (the reference itself is pure
 # Python and does not travel to the GPU box; oracle/evac_oracle.py is proven bit-identical to it).
-def _cpu_worker(args):
+def _cpu_worker(args, n_ped=None):
     n_envs, steps, warmup, seed, barrier = args
     from oracle.evac_oracle import OracleConfig, OracleEnv
 
-    cfg = OracleConfig(**ENV_KW, **WRAP_KW)
+    kw = dict(ENV_KW) if n_ped is None else dict(ENV_KW, number_of_pedestrians=n_ped)
+    cfg = OracleConfig(**kw, **WRAP_KW)
     envs = []
     np.random.seed(seed)
     for _ in range(n_envs):
@@ -155,9 +156,13 @@ def cpu_baseline_single_core(target_seconds=12.0):
     steps = min(steps, 200000)
     t = _cpu_worker((1, steps, 20, 0, None))
     env_sps = steps / t
+    # the large-crowd config (C4) on one core, 1 env x 4096 pedestrians, a handful of steps (~1 step/s)
+    t4 = _cpu_worker((1, 5, 1, 0, None), n_ped=4096)
     return {"value": env_sps * N_PED, "unit": "pedestrian-steps/s", "env_steps_per_s": env_sps, "cores": 1, "kind": "port",
             "sample": f"oracle/evac_oracle.py (NumPy fp64 port, bit-identical to the reference on tests/golden), 1 env x {N_PED} pedestrians, "
-                      f"{steps} steps in {t:.1f} s on 1 core, rel+ohe Box observation"}
+                      f"{steps} steps in {t:.1f} s on 1 core, rel+ohe Box observation",
+            "c4_1x4096": {"value": 5 * 4096 / t4, "unit": "pedestrian-steps/s", "env_steps_per_s": 5 / t4,
+                          "sample": f"1 env x 4096 pedestrians, 5 steps in {t4:.1f} s on 1 core"}}
 
 
 def run_reference_arm(args):
@@ -228,7 +233,11 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     E, K, W = args.envs, args.steps, max(args.warmup, 3)
 
-    from evacuation_b200.distributed import allgather_episode_totals, shard_offset
+    from evacuation_b200.distributed import allgather_episode_totals, bind_host_to_device, shard_offset
+
+    # one process per GPU: run on the cores of the GPU's own socket so that the page-locked buffers of the e2e leg are
+    # local to it (EVAC_BENCH_NO_NUMA_BIND=1 switches this off for A/B runs)
+    numa = {"bound": False} if os.environ.get("EVAC_BENCH_NO_NUMA_BIND") else bind_host_to_device(local_rank)
 
     env = eb.setup_env(eb.EnvConfig(**ENV_KW), eb.EnvWrappersConfig(**WRAP_KW), num_envs=E, device=dev, seed=args.seed,
                        auto_reset=True, env_index_offset=shard_offset(rank, E))
@@ -275,6 +284,10 @@ def run_ours(args):
     graph_a.replay()  # untimed: graph upload + one more pass over every set
     barrier()
     sampler.start()
+    # device head start: the GPU spins while the host submits the K-node graph launch, so the event pair brackets device
+    # execution only (the host-side launch of a large graph takes a few hundred microseconds before its first node runs)
+    if not os.environ.get("EVAC_BENCH_NO_HEADSTART"):
+        torch.cuda._sleep(int((1e-3 + 1e-6 * K) * 1.9e9))
     e0.record()
     graph_a.replay()
     e1.record()
@@ -397,7 +410,8 @@ def run_ours(args):
                         "note": "K steps in ONE launch (evac_rollout), on-device RandomAgent, obs written after the last step"},
             "e2e": {"value": env_steps * N_PED / e2e_s, "unit": "pedestrian-steps/s", "h2d_bytes_per_step": E * 8,
                     "d2h_bytes_per_step": E * (obs_dim * 4 + 4 + 1 + 1), "ms_per_step": 1e3 * e2e_s / K,
-                    "api": "setup_env(..., batched=False).step(numpy actions) -> numpy obs, reward, flags (evac_step_host)"},
+                    "api": "setup_env(..., batched=False).step(numpy actions) -> numpy obs, reward, flags (evac_step_host)",
+                    "host_affinity": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "us_per_step_by_rank": per_rank_us,

@@ -9,6 +9,34 @@ import torch.distributed as dist
 from ._native import EPISODE_STAT_KEYS, NUM_EPISODE_STATS
 
 
+def bind_host_to_device(device_index: int) -> dict:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (its NUMA node / socket).
+
+    Opt-in, for the host face (`evac_step_host`: NumPy in / NumPy out) under one process per GPU: page-locked buffers
+    allocated afterwards are first-touched on the GPU's own socket, so the per-step D2H copy of the observation block
+    (1.5 KB per environment) does not cross the inter-socket link; with 8 ranks copying at once an unbound rank whose
+    buffers sit on the other socket is bound by that link, not by its PCIe lanes.  Returns what was done (never raises:
+    without NVML or on a single-node host it is a no-op)."""
+    import os
+
+    info = {"bound": False}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        info.update(bound=True, cpus=len(cpus), first_cpu=min(cpus), last_cpu=max(cpus))
+    except Exception as exc:  # NVML missing, cpuset restrictions, non-Linux: leave the affinity alone
+        info["reason"] = repr(exc)
+    return info
+
+
 def shard_offset(rank: int, envs_per_rank: int) -> int:
     """Global index of this rank's first environment; passed as `env_index_offset` so every
     environment draws the same Philox streams regardless of the number of ranks."""

@@ -48,9 +48,16 @@ struct WPed {
   int st;       // status (ST_NONE for padding lanes)
 };
 
+#ifndef EVAC_WARP_MINB
+// resident warps per SM the register allocation is sized for.  28 -> 70 registers per thread, no spills in the step loop, and
+// still 29 warps per SM: the headline batch (4096 envs = 27.7 warps per SM) stays one wave.  Measured on B200 against 32
+// (64 registers, 8 bytes spilled per step): 9.23 -> 8.90 us per 4096-env step, 5.11 -> 4.92 us in-rollout; 24 (76 registers,
+// 26 warps per SM) pushes 4096 envs into a second wave: 9.81 us.
+#define EVAC_WARP_MINB 28
+#endif
 // WPC = environments (independent warps) per CTA: fewer, fatter CTAs for the block scheduler; no block-level barrier anywhere.
 template <int MODE, int WPC>
-__global__ void __launch_bounds__(32 * WPC, 32 / WPC) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
+__global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
   __shared__ __align__(16) float4 tile_all[WPC][66];  // Tile<float> of 64 slots (+ the look-ahead entries) per warp
   // strip culling (a.cells_x > 0): the sources are sorted by vertical strip (edge >= vision radius) so that a
   // pedestrian only visits the slots of its own and the two adjacent strips

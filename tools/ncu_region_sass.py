@@ -37,7 +37,7 @@ for r in rows:
         continue
     if r[0] == "Function Name":
         if first_fn is None and (want is None or want in r[1]):
-            first_fn = r[1]
+            first_fn, KERNEL_FILE = r[1], cur_file
         skip = r[1] != first_fn
         continue
     if r[0] == "Line No":

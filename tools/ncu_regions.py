@@ -1,6 +1,6 @@
 """Executed warp-instructions of the step kernel grouped by code region (source-line ranges of
 evac_kernels.cuh), from `ncu -i X.ncu-rep --page source --csv --print-source cuda,sass`.
-Usage: ... | python tools/ncu_regions.py <warps-launched> """
+Usage: ... | python tools/ncu_regions.py <warps-launched> [kernel-substring]"""
 import csv
 import re
 import sys
@@ -8,6 +8,7 @@ from collections import defaultdict
 
 rows = list(csv.reader(sys.stdin))
 warps = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+want = sys.argv[2] if len(sys.argv) > 2 else None  # optional kernel-name substring (default: the first kernel of the report)
 # region markers: a line `// @region name` in a .cuh starts a region (until the next marker)
 OWN = ("evac_kernels.cuh", "evac_warp.cuh")
 marks = {f: [(i + 1, m.group(1)) for i, l in enumerate(open("evacuation_b200/csrc/" + f).read().splitlines())
@@ -40,8 +41,8 @@ for r in rows:
         cur_file = r[1].split("/")[-1]
         continue
     if r[0] == "Function Name":
-        if first_fn is None:
-            first_fn = r[1]
+        if first_fn is None and (want is None or want in r[1]):
+            first_fn, KERNEL_FILE = r[1], cur_file
         skip = r[1] != first_fn
         continue
     if r[0] == "Line No":

@@ -70,6 +70,7 @@ struct EvacHandle {
   int threads = 0, ppt = 0;
   int num_sms = 0;
   int cells_x = 0, cells_y = 0, cell_reach = 1;  // > 0: cell-list neighbour search (multi-warp fp32 shapes)
+  int cell_pair_walk = 1;        // paired walk of the sorted slots (EVAC_CELL_PAIR_WALK=0: one slot per thread)
   bool warp_kernel = true;       // N <= 64 fp32: evac_warp_kernel (false: the generic kernel, EVAC_WARP_KERNEL=generic)
   int warps_per_cta = 1;         // environments per CTA of evac_warp_kernel (EVAC_WARP_WPC = 1 | 2 | 4 | 8)
 };
@@ -110,7 +111,7 @@ static KArgs<real> make_args(const EvacHandle* h) {
   a.eps_f = (float)c.eps; a.enslaving_f = (float)c.enslaving_degree;
   a.thr2_ped = thr2_of<real>(c.to_pedestrian); a.thr2_leader = thr2_of<real>(c.to_leader);
   a.thr2_exit = thr2_of<real>(c.to_exit); a.thr2_escape = thr2_of<real>(c.to_escape);
-  a.cells_x = h->cells_x; a.cells_y = h->cells_y; a.cell_reach = h->cell_reach;
+  a.cells_x = h->cells_x; a.cells_y = h->cells_y; a.cell_reach = h->cell_reach; a.cell_pair_walk = h->cell_pair_walk;
   a.cell_inv_x = h->cells_x > 0 ? (float)(h->cells_x / (2.0 * c.width)) : 0.f;
   a.cell_inv_y = h->cells_y > 0 ? (float)(h->cells_y / (2.0 * c.height)) : 0.f;
   a.exit_reward = c.is_new_exiting_reward; a.follow_reward = c.is_new_followers_reward;
@@ -289,6 +290,11 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
     if (2.0 * cfg->width / edge > 64.0 || 2.0 * cfg->height / edge > 64.0) { reach = 1; edge = cfg->to_pedestrian * (1.0 + 1e-4); }
     const int gx = (int)fmin(64.0, floor(2.0 * cfg->width / edge)), gy = (int)fmin(64.0, floor(2.0 * cfg->height / edge));
     if (gx >= 1 && gy >= 1 && (cfg->neighbor_search == EVAC_SEARCH_CELLS || gx * gy >= 16)) { h->cells_x = gx; h->cells_y = gy; h->cell_reach = reach; }
+    // paired walk (two adjacent sorted slots per thread share one window): pays when neighbouring slots usually share a cell.
+    // Measured on B200, 20 steps after 0 / 64 / 300 warm-up steps: 256 x 4096 (2.7 per cell) 144 / 177 / 271 -> 129 / 167 / 265 us,
+    // 1024 x 1000 109 -> 107 us, 2048 x 256 (0.17 per cell) 58 -> 63 us  => on from half a pedestrian per cell
+    h->cell_pair_walk = 2 * h->N >= gx * gy;
+    { const char* pw = getenv("EVAC_CELL_PAIR_WALK"); if (pw) h->cell_pair_walk = atoi(pw) != 0; }
   } else if (h->threads == 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search == EVAC_SEARCH_CELLS) {
     // one-warp kernel, opt-in: vertical strips (a 1-D cell list, at most 32 strips), same edge rule.  Measured on
     // B200 (profiles/README.md): 15 % fewer instructions than the all-pairs tile but no wall-clock gain (the warp is

@@ -58,6 +58,7 @@ struct KArgs {
   // uniform cell grid of the neighbour search (multi-warp shapes, float32): cells_x * cells_y cells of edge
   // >= vision radius over [-width,width] x [-height,height]; cells_x == 0 -> brute-force tiled pass
   int cells_x, cells_y, cell_reach;  // neighbours within `cell_reach` cells (cell edge >= radius / cell_reach)
+  int cell_pair_walk;                // cell_list_pass step 5: two adjacent sorted slots of one cell row per thread (shared window)
   float cell_inv_x, cell_inv_y;      // cells per unit length
   int exit_reward, follow_reward, term_wall;
   real init_reward, intrinsic_coef;
@@ -303,8 +304,9 @@ struct CellSmem {
   uint16_t* sorted_idx;  // [SLOTS]  original index | 0x8000 if VISCEK/FOLLOWER
   int* cell_start;       // [C + 1]
   int* warp_tot;         // [32]
+  int* row_pairs;        // [cells_y + 1 <= 65]  paired walk: number of slot pairs in the cell rows below (exclusive scan)
   static __host__ __device__ constexpr size_t bytes(int slots, int cells) {
-    return (size_t)slots * 8 + (size_t)slots * 2 + (((size_t)cells + 1 + 3) & ~(size_t)3) * 4 + 32 * 4;
+    return (size_t)slots * 8 + (size_t)slots * 2 + (((size_t)cells + 1 + 3) & ~(size_t)3) * 4 + (32 + 68) * 4;
   }
   __device__ __forceinline__ CellSmem(unsigned char* base, int slots, int cells) {
     res = reinterpret_cast<float2*>(base);
@@ -312,6 +314,7 @@ struct CellSmem {
     sorted_idx = reinterpret_cast<uint16_t*>(base + (size_t)slots * 8);
     cell_start = reinterpret_cast<int*>(base + (size_t)slots * 10);
     warp_tot = cell_start + ((cells + 1 + 3) & ~3);
+    row_pairs = warp_tot + 32;
   }
 };
 
@@ -433,9 +436,96 @@ __device__ __forceinline__ void cell_list_pass(const Tile<float>& tile, const Ce
     }
   }
   if (tid < 2) tile.put(n_src + tid, PARK, PARK, 0.f, 0.f);  // pad to an even count (the tile has 2 spare slots)
+  if (a.cell_pair_walk && warp == 0) {
+    // slot pairs per cell row (a pair never straddles two rows), exclusive scan over the <= 64 rows by one warp
+    int cnt[2], inc = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = lane + 32 * k;
+      cnt[k] = r < a.cells_y ? (cs.cell_start[(r + 1) * a.cells_x] - cs.cell_start[r * a.cells_x] + 1) >> 1 : 0;
+    }
+    int run = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      inc = cnt[k];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      const int r = lane + 32 * k;
+      if (r <= a.cells_y) cs.row_pairs[r] = run + inc - cnt[k];
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0 && a.cells_y == 64) cs.row_pairs[64] = run;
+  }
   __syncthreads();  // list[] (aliased by res[]) is dead from here on
   // ---- 5. walk the sorted slots
   const float thr2 = a.thr2_ped;
+  if (a.cell_pair_walk) {
+    // Two adjacent sorted slots of ONE cell row per thread: they sit in the same or in neighbouring cells, so one walk over
+    // the union of their windows serves both -- every loaded source pair is evaluated against two pedestrians (half the
+    // LDS per evaluated pair, like the 2-pedestrians-per-lane all-pairs pass).  A slot outside a pedestrian's own window
+    // fails the distance test and adds an exact zero, so the sums equal the one-slot walk bit for bit.
+    const int reach = a.cell_reach;
+    const int n_pairs = cs.row_pairs[a.cells_y];
+#pragma unroll 1
+    for (int t = tid; t < n_pairs; t += THREADS) {
+      int row = 0;
+      {  // largest row with row_pairs[row] <= t
+        int hi_r = a.cells_y;
+        while (hi_r - row > 1) { const int mid = (row + hi_r) >> 1; if (cs.row_pairs[mid] <= t) row = mid; else hi_r = mid; }
+      }
+      const int row_end = cs.cell_start[(row + 1) * a.cells_x];
+      const int s0 = cs.cell_start[row * a.cells_x] + 2 * (t - cs.row_pairs[row]);
+      const bool two = s0 + 1 < row_end;
+      const int id0 = cs.sorted_idx[s0], id1 = two ? cs.sorted_idx[s0 + 1] : 0;
+      if (!((id0 | id1) & 0x8000)) continue;
+      const float4 p0 = tile.P2[s0 >> 1];
+      const float x0 = (s0 & 1) ? p0.y : p0.x, y0 = (s0 & 1) ? p0.w : p0.z;
+      float x1 = x0, y1 = y0;
+      if (two) { const float4 p1 = tile.P2[(s0 + 1) >> 1]; x1 = ((s0 + 1) & 1) ? p1.y : p1.x; y1 = ((s0 + 1) & 1) ? p1.w : p1.z; }
+      int cxa, cxb, cy_;
+      cell_of(x0, y0, a, cxa, cy_);
+      cell_of(x1, y1, a, cxb, cy_);
+      const int cx0 = max(min(cxa, cxb) - reach, 0), cx1 = min(max(cxa, cxb) + reach, a.cells_x - 1);
+      const float2 nx0 = make_float2(-x0, -x0), ny0 = make_float2(-y0, -y0), nx1 = make_float2(-x1, -x1), ny1 = make_float2(-y1, -y1);
+      float2 ax0 = make_float2(0.f, 0.f), ay0 = ax0, ax1 = ax0, ay1 = ax0;
+      int done = 0;
+      for (int r = max(row - reach, 0); r <= min(row + reach, a.cells_y - 1); ++r) {
+        const int lo = max(cs.cell_start[r * a.cells_x + cx0] & ~1, done);
+        const int hi = (cs.cell_start[r * a.cells_x + cx1 + 1] + 1) & ~1;
+        int j = lo >> 1;
+        const int je = hi >> 1;
+        if (j < je) {
+          float4 p = tile.P2[j], u = tile.U2[j];
+#pragma unroll 2
+          for (; j < je; ++j) {
+            const float4 pn = tile.P2[j + 1], un = tile.U2[j + 1];
+            const float2 sxp = make_float2(p.x, p.y), syp = make_float2(p.z, p.w), sux = make_float2(u.x, u.y), suy = make_float2(u.z, u.w);
+            {
+              const float2 dx = __fadd2_rn(sxp, nx0), dy = __fadd2_rn(syp, ny0);
+              float2 d2 = __fmul2_rn(dx, dx);
+              d2 = __ffma2_rn(dy, dy, d2);
+              const float2 w = make_float2(d2.x < thr2 ? 1.f : 0.f, d2.y < thr2 ? 1.f : 0.f);
+              ax0 = __ffma2_rn(w, sux, ax0);
+              ay0 = __ffma2_rn(w, suy, ay0);
+            }
+            {
+              const float2 dx = __fadd2_rn(sxp, nx1), dy = __fadd2_rn(syp, ny1);
+              float2 d2 = __fmul2_rn(dx, dx);
+              d2 = __ffma2_rn(dy, dy, d2);
+              const float2 w = make_float2(d2.x < thr2 ? 1.f : 0.f, d2.y < thr2 ? 1.f : 0.f);
+              ax1 = __ffma2_rn(w, sux, ax1);
+              ay1 = __ffma2_rn(w, suy, ay1);
+            }
+            p = pn;
+            u = un;
+          }
+        }
+        done = max(done, hi);
+      }
+      if (id0 & 0x8000) cs.res[id0 & 0x7fff] = make_float2(ax0.x + ax0.y, ay0.x + ay0.y);
+      if (id1 & 0x8000) cs.res[id1 & 0x7fff] = make_float2(ax1.x + ax1.y, ay1.x + ay1.y);
+    }
+  } else {
 #pragma unroll 1
   for (int s = tid; s < n_src; s += THREADS) {
     const int id = cs.sorted_idx[s];
@@ -475,6 +565,7 @@ __device__ __forceinline__ void cell_list_pass(const Tile<float>& tile, const Ce
       done = max(done, hi);
     }
     cs.res[id & 0x7fff] = make_float2(ax.x + ax.y, ay.x + ay.y);
+  }
   }
   __syncthreads();
   // ---- 6. back to the owners

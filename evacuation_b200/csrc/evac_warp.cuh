@@ -55,6 +55,9 @@ struct WPed {
 // 26 warps per SM) pushes 4096 envs into a second wave: 9.81 us.
 #define EVAC_WARP_MINB 28
 #endif
+#ifndef EVAC_PAIR_UNROLL
+#define EVAC_PAIR_UNROLL 4  // slot pairs per unrolled iteration of the pairwise loop
+#endif
 // WPC = environments (independent warps) per CTA: fewer, fatter CTAs for the block scheduler; no block-level barrier anywhere.
 template <int MODE, int WPC>
 __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
       for (int k = 0; k < 2; ++k) windowed_pass(tile, win_lo[k], win_hi[k], q[k].p.x, q[k].p.y, a.thr2_ped, sx[k], sy[k]);
     } else {
       const float xi[2] = {q[0].p.x, q[1].p.x}, yi[2] = {q[0].p.y, q[1].p.y};
-      if (__any_sync(0xffffffffu, fv[0] | fv[1])) pairwise_pass<2, false>(tile, n_src, xi, yi, a.thr2_ped, sx, sy, cnt);
+      if (__any_sync(0xffffffffu, fv[0] | fv[1])) pairwise_pass<2, false, EVAC_PAIR_UNROLL>(tile, n_src, xi, yi, a.thr2_ped, sx, sy, cnt);
       else sx[0] = sx[1] = sy[0] = sy[1] = 0.f;
     }
     // ---------------- new headings, enslaving, integration, reflection, statuses  // @region wupdate

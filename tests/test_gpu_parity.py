@@ -283,6 +283,46 @@ def test_cell_list_equals_all_pairs_search(n, width, height, vision, monkeypatch
     np.testing.assert_allclose(out["cells"]["rew"], out["brute"]["rew"], rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("n,width,height,vision", [(4096, 1.0, 1.0, 0.1), (1000, 1.5, 0.8, 0.1), (300, 1.0, 1.0, 0.35), (2048, 1.0, 1.0, 0.011), (129, 1.0, 1.0, 0.1)])
+def test_cell_list_paired_walk_is_bit_identical_to_the_single_slot_walk(n, width, height, vision, monkeypatch):
+    """cell_list_pass step 5 has two walks of the sorted slots: one slot per thread, or two adjacent slots of one cell row
+    sharing the union of their windows (the default from half a pedestrian per cell).  A slot outside a pedestrian's own
+    window fails the distance test and adds an exact zero, so both walks must give the same bits -- states, rewards and
+    observations -- over a free-running rollout, dense cluster and odd row lengths included."""
+    import evacuation_b200 as eb
+
+    monkeypatch.setattr(eb.SwitchDistances, "to_pedestrian", vision)
+    E, steps = 3, 10
+    env_kw = dict(number_of_pedestrians=n, width=width, height=height, is_new_exiting_reward=True, intrinsic_reward_coef=0.3,
+                  enslaving_degree=0.6, noise_coef=0.4)
+    wrap = dict(positions="rel", statuses="ohe", type="Box")
+    rs = np.random.RandomState(7 + n)
+    pos = rs.uniform(-1, 1, (E, n, 2)) * np.array([width, height])
+    pos[1, : n // 2] = np.array([-0.4 * width, 0.5 * height]) + rs.normal(0, 0.03, (n // 2, 2))
+    pos = np.clip(pos, [-width, -height], [width, height])
+    ang = rs.uniform(0, 2 * np.pi, (E, n))
+    dirs = np.stack([np.cos(ang), np.sin(ang)], axis=-1)
+    actions = rs.uniform(-1, 1, (steps, E, 2)).astype(np.float32)
+    out = {}
+    for walk in ("0", "1"):
+        monkeypatch.setenv("EVAC_CELL_PAIR_WALK", walk)
+        env = _make_env(env_kw, wrap, E, neighbor_search="cells")
+        u = env.unwrapped
+        u.reset()
+        u.set_state(positions=pos, directions=dirs, agent_position=np.zeros((E, 2), np.float32), agent_direction=np.zeros((E, 2), np.float32),
+                    now=np.zeros(E, np.int32))
+        rew = []
+        for s in range(steps):
+            obs, r, _, _, _ = env.step(torch.as_tensor(actions[s]))
+            rew.append(r.cpu().numpy().copy())
+        st = u.get_state()
+        out[walk] = dict(pos=st["positions"].cpu().numpy(), dir=st["directions"].cpu().numpy(), st=st["statuses"].cpu().numpy(),
+                         rew=np.array(rew), obs=obs.cpu().numpy().copy())
+        u.close()
+    for k in ("pos", "dir", "st", "rew", "obs"):
+        assert np.array_equal(out["0"][k], out["1"][k], equal_nan=True), k
+
+
 def test_cell_list_nan_poisoning_matches_all_pairs():
     """A zero direction (0/0 = NaN unit vector, area.py:101) poisons EVERY neighbour sum in the reference; the cell
     list must reproduce that, not only for the pedestrians whose cells contain the NaN source."""

@@ -166,7 +166,8 @@ static void pick_shape(int n, int* threads, int* ppt) {
   else if (n <= 512) { *threads = 256; *ppt = 2; }
   else if (n <= 1024) { *threads = 512; *ppt = 2; }
   else if (n <= 2048) { *threads = 512; *ppt = 4; }
-  else { *threads = 1024; *ppt = 4; }
+  else if (n <= 4096) { *threads = 1024; *ppt = 4; }
+  else { *threads = 1024; *ppt = 8; }  // up to 8192: the sorted tile (16 B per pedestrian) + cell list still fit one SM's shared memory
 }
 
 // N <= 64, float32: the dedicated one-warp kernel (evac_warp.cuh), observation encoding resolved at compile time.
@@ -204,6 +205,9 @@ static int launch_step(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
     case 512 * 16 + 2: return launch_step_t<real, 512, 2>(h, a, st);
     case 512 * 16 + 4: return launch_step_t<real, 512, 4>(h, a, st);
     case 1024 * 16 + 4: return launch_step_t<real, 1024, 4>(h, a, st);
+    case 1024 * 16 + 8:
+      if constexpr (std::is_same<real, float>::value) return launch_step_t<real, 1024, 8>(h, a, st);
+      break;  // fp64 parity mode: 32 B per tile slot, N <= 4096
   }
   return fail(EVAC_ERR_INVALID, "no kernel shape for N=%d", h->N);
 }
@@ -249,8 +253,10 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   *out = nullptr;
   if (cfg->abi_version != EVAC_ABI_VERSION) return fail(EVAC_ERR_INVALID, "EvacConfig.abi_version %d != %d", cfg->abi_version, EVAC_ABI_VERSION);
   if (num_envs < 1) return fail(EVAC_ERR_INVALID, "num_envs must be >= 1");
-  if (cfg->number_of_pedestrians < 1 || cfg->number_of_pedestrians > 4096)
-    return fail(EVAC_ERR_INVALID, "number_of_pedestrians=%d outside the supported range 1..4096", cfg->number_of_pedestrians);
+  if (cfg->number_of_pedestrians < 1 || cfg->number_of_pedestrians > 8192)
+    return fail(EVAC_ERR_INVALID, "number_of_pedestrians=%d outside the supported range 1..8192", cfg->number_of_pedestrians);
+  if (cfg->number_of_pedestrians > 4096 && cfg->precision == EVAC_PREC_F64)
+    return fail(EVAC_ERR_INVALID, "number_of_pedestrians=%d: the fp64 parity mode supports 1..4096 (32 B per shared-memory tile slot)", cfg->number_of_pedestrians);
   if (cfg->positions < 0 || cfg->positions > 2 || cfg->statuses < 0 || cfg->statuses > 2 || cfg->obs_type < 0 || cfg->obs_type > 1)
     return fail(EVAC_ERR_INVALID, "invalid observation mode");  // ValueError in the reference (wrappers.py:45,75)
   if (cfg->positions == EVAC_POS_GRAV && cfg->obs_type == EVAC_OBS_BOX)
@@ -288,7 +294,12 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
     int reach = (rs && atoi(rs) == 1) ? 1 : 2;
     double edge = cfg->to_pedestrian * (1.0 + 1e-4) / reach;
     if (2.0 * cfg->width / edge > 64.0 || 2.0 * cfg->height / edge > 64.0) { reach = 1; edge = cfg->to_pedestrian * (1.0 + 1e-4); }
-    const int gx = (int)fmin(64.0, floor(2.0 * cfg->width / edge)), gy = (int)fmin(64.0, floor(2.0 * cfg->height / edge));
+    int gx = (int)fmin(64.0, floor(2.0 * cfg->width / edge)), gy = (int)fmin(64.0, floor(2.0 * cfg->height / edge));
+    {  // the sorted tile + cell list of one environment live in ONE SM's shared memory: coarsen the grid (larger cells stay
+       // valid) until they fit -- only reached above 4096 pedestrians with a grid near the 64 x 64 cap
+      const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 4096 /* static */, slots = (size_t)h->threads * h->ppt;
+      while (gx * gy > 16 && Tile<float>::bytes((int)slots) + CellSmem::bytes((int)slots, gx * gy) > budget) { gx = (gx * 7 + 7) / 8; gy = (gy * 7 + 7) / 8; }
+    }
     if (gx >= 1 && gy >= 1 && (cfg->neighbor_search == EVAC_SEARCH_CELLS || gx * gy >= 16)) { h->cells_x = gx; h->cells_y = gy; h->cell_reach = reach; }
     // paired walk (two adjacent sorted slots per thread share one window): pays when neighbouring slots usually share a cell.
     // Measured on B200, 20 steps after 0 / 64 / 300 warm-up steps: 256 x 4096 (2.7 per cell) 144 / 177 / 271 -> 129 / 167 / 265 us,

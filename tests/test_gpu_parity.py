@@ -236,7 +236,7 @@ def test_kernel_shapes_random_states(n, num_envs, steps, wrap, search):
 
 
 @pytest.mark.parametrize("n,width,height,vision", [(60, 1.0, 1.0, 0.1), (64, 1.5, 0.8, 0.1), (33, 1.0, 1.0, 0.3), (4096, 1.0, 1.0, 0.1), (1000, 1.5, 0.8, 0.1), (300, 1.0, 1.0, 0.35), (2048, 1.0, 1.0, 0.011), (200, 1.0, 1.0, 0.9),
-                                                   (500, 0.3, 0.3, 0.1)])
+                                                   (500, 0.3, 0.3, 0.1), (8192, 1.0, 1.0, 0.1), (6000, 1.0, 1.0, 0.02)])
 def test_cell_list_equals_all_pairs_search(n, width, height, vision, monkeypatch):
     """Large crowds (BASELINE config 4): the cell-list neighbour search evaluates the same predicate on a superset
     of the contributing pairs, so a free-running rollout must retrace the all-pairs kernel (only the float32
@@ -283,7 +283,8 @@ def test_cell_list_equals_all_pairs_search(n, width, height, vision, monkeypatch
     np.testing.assert_allclose(out["cells"]["rew"], out["brute"]["rew"], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("n,width,height,vision", [(4096, 1.0, 1.0, 0.1), (1000, 1.5, 0.8, 0.1), (300, 1.0, 1.0, 0.35), (2048, 1.0, 1.0, 0.011), (129, 1.0, 1.0, 0.1)])
+@pytest.mark.parametrize("n,width,height,vision", [(4096, 1.0, 1.0, 0.1), (1000, 1.5, 0.8, 0.1), (300, 1.0, 1.0, 0.35), (2048, 1.0, 1.0, 0.011), (129, 1.0, 1.0, 0.1),
+                                                   (8192, 1.0, 1.0, 0.1)])
 def test_cell_list_paired_walk_is_bit_identical_to_the_single_slot_walk(n, width, height, vision, monkeypatch):
     """cell_list_pass step 5 has two walks of the sorted slots: one slot per thread, or two adjacent slots of one cell row
     sharing the union of their windows (the default from half a pedestrian per cell).  A slot outside a pedestrian's own
@@ -321,6 +322,26 @@ def test_cell_list_paired_walk_is_bit_identical_to_the_single_slot_walk(n, width
         u.close()
     for k in ("pos", "dir", "st", "rew", "obs"):
         assert np.array_equal(out["0"][k], out["1"][k], equal_nan=True), k
+
+
+def test_pedestrian_count_limits():
+    """1 .. 8192 pedestrians per environment in float32 (the sorted tile + cell list of one environment must fit one SM's
+    shared memory), 1 .. 4096 in the fp64 parity mode; anything else fails loudly at creation."""
+    import evacuation_b200 as eb
+
+    wrap = eb.EnvWrappersConfig(positions="rel", statuses="ohe", type="Box")
+    with pytest.raises(ValueError, match="8192"):
+        eb.setup_env(eb.EnvConfig(number_of_pedestrians=8193), wrap, num_envs=2, batched=True).reset()
+    with pytest.raises(ValueError, match="fp64"):
+        eb.setup_env(eb.EnvConfig(number_of_pedestrians=5000), wrap, num_envs=2, batched=True, precision="fp64").reset()
+    env = eb.setup_env(eb.EnvConfig(number_of_pedestrians=8192), wrap, num_envs=2, batched=True)
+    obs, _ = env.reset()
+    assert tuple(obs.shape) == (2, 8194, 6)
+    obs, r, term, trunc, _ = env.step(torch.zeros((2, 2), device="cuda") + 0.5)
+    assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(r).all())
+    st = env.unwrapped.get_state()
+    assert float(st["positions"].abs().max()) <= 1.0
+    env.unwrapped.close()
 
 
 def test_cell_list_nan_poisoning_matches_all_pairs():

@@ -71,6 +71,7 @@ struct EvacHandle {
   int num_sms = 0;
   int cells_x = 0, cells_y = 0, cell_reach = 1;  // > 0: cell-list neighbour search (multi-warp fp32 shapes)
   int cell_pair_walk = 1;        // paired walk of the sorted slots (EVAC_CELL_PAIR_WALK=0: one slot per thread)
+  int cluster = 1;               // > 1: one environment per thread-block cluster of this many 1024 x 4 CTAs (N > 4096, evac_cluster.cuh)
   bool warp_kernel = true;       // N <= 64 fp32: evac_warp_kernel (false: the generic kernel, EVAC_WARP_KERNEL=generic)
   int warps_per_cta = 1;         // environments per CTA of evac_warp_kernel (EVAC_WARP_WPC = 1 | 2 | 4 | 8)
 };
@@ -157,6 +158,34 @@ static int launch_step_t(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
   return EVAC_OK;
 }
 
+// One environment per cluster of CL CTAs (crowds above one SM's shared memory): grid = E x CL, cluster dimension as a
+// launch attribute.
+template <int CL>
+static int launch_cluster_t(EvacHandle* h, const KArgs<float>& a, cudaStream_t st) {
+  constexpr int THREADS = 1024, PPT = 4;
+  const int C = a.cells_x * a.cells_y;
+  const size_t smem = Tile<float>::bytes(THREADS * PPT) + CellSmem::bytes(THREADS * PPT, C) + ClusterSmem::bytes(C);
+  static thread_local size_t attr_set[16] = {0};
+  auto kern = evac_step_kernel<float, THREADS, PPT, CL>;
+  if (attr_set[h->device & 15] < smem) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[h->device & 15] = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)a.E * CL);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, a));
+  h->launches++;
+  return EVAC_OK;
+}
+
 static void pick_shape(int n, int* threads, int* ppt) {
   const char* shape = getenv("EVAC_SHAPE_64");  // A/B switch for N <= 64: "64x1" or "32x2" (default)
   if (n <= 64 && shape && strcmp(shape, "64x1") == 0) { *threads = 64; *ppt = 1; }
@@ -195,6 +224,11 @@ template <typename real>
 static int launch_step(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
   if constexpr (std::is_same<real, float>::value) {
     if (h->threads == 32 && h->warp_kernel) return launch_warp(h, a, st);
+    switch (h->cluster) {
+      case 2: return launch_cluster_t<2>(h, a, st);
+      case 4: return launch_cluster_t<4>(h, a, st);
+      case 8: return launch_cluster_t<8>(h, a, st);
+    }
   }
   switch (h->threads * 16 + h->ppt) {
     case 32 * 16 + 2: return launch_step_t<real, 32, 2>(h, a, st);
@@ -253,8 +287,11 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   *out = nullptr;
   if (cfg->abi_version != EVAC_ABI_VERSION) return fail(EVAC_ERR_INVALID, "EvacConfig.abi_version %d != %d", cfg->abi_version, EVAC_ABI_VERSION);
   if (num_envs < 1) return fail(EVAC_ERR_INVALID, "num_envs must be >= 1");
-  if (cfg->number_of_pedestrians < 1 || cfg->number_of_pedestrians > 8192)
-    return fail(EVAC_ERR_INVALID, "number_of_pedestrians=%d outside the supported range 1..8192", cfg->number_of_pedestrians);
+  if (cfg->number_of_pedestrians < 1 || cfg->number_of_pedestrians > 32768)
+    return fail(EVAC_ERR_INVALID, "number_of_pedestrians=%d outside the supported range 1..32768", cfg->number_of_pedestrians);
+  if (cfg->number_of_pedestrians > 8192 && cfg->neighbor_search == EVAC_SEARCH_BRUTE)
+    return fail(EVAC_ERR_INVALID, "number_of_pedestrians=%d: the all-pairs search keeps one environment in one SM's shared memory (1..8192); "
+                                  "larger crowds run the clustered cell list", cfg->number_of_pedestrians);
   if (cfg->number_of_pedestrians > 4096 && cfg->precision == EVAC_PREC_F64)
     return fail(EVAC_ERR_INVALID, "number_of_pedestrians=%d: the fp64 parity mode supports 1..4096 (32 B per shared-memory tile slot)", cfg->number_of_pedestrians);
   if (cfg->positions < 0 || cfg->positions > 2 || cfg->statuses < 0 || cfg->statuses > 2 || cfg->obs_type < 0 || cfg->obs_type > 1)
@@ -283,6 +320,21 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
   h->obs_dim = compute_obs_dim(*cfg); h->prec = cfg->precision; h->seed = seed; h->env_offset = env_index_offset;
   h->num_sms = prop.multiProcessorCount;
   pick_shape(h->N, &h->threads, &h->ppt);
+  if (h->N > 64 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search != EVAC_SEARCH_BRUTE) {
+    // above the 8192 pedestrians one SM's shared memory holds: a cluster of 4 / 8 CTAs (1024 threads x 4 pedestrians) per
+    // environment.  EVAC_CLUSTER = 1 | 2 | 4 | 8 overrides the choice where the crowd fits (A/B measurements, cluster-size
+    // invariance tests).  Measured on B200 (10 steps after 32): 128 x 8192 one 1024 x 8 CTA 226 us, cluster of 2 263 us;
+    // 256 x 4096 one CTA 161 us, cluster of 2 288 us -> clusters only where one CTA cannot hold the crowd.
+    int want = h->N <= 8192 ? 1 : (h->N <= 16384 ? 4 : 8);
+    const char* cl = getenv("EVAC_CLUSTER");
+    if (cl) {
+      const int v = atoi(cl);
+      if ((v == 2 || v == 4 || v == 8) && v * 4096 >= h->N) want = v;
+      if (v == 1 && h->N <= 8192) want = 1;
+    }
+    h->cluster = want;
+    if (h->cluster > 1) { h->threads = 1024; h->ppt = 4; }
+  }
   { const char* wk = getenv("EVAC_WARP_KERNEL"); h->warp_kernel = !(wk && strcmp(wk, "generic") == 0); }
   { const char* wp = getenv("EVAC_WARP_WPC"); if (wp) h->warps_per_cta = atoi(wp); }
   if (h->N > 64 && h->threads > 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search != EVAC_SEARCH_BRUTE) {
@@ -299,8 +351,10 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
        // valid) until they fit -- only reached above 4096 pedestrians with a grid near the 64 x 64 cap
       const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 4096 /* static */, slots = (size_t)h->threads * h->ppt;
       while (gx * gy > 16 && Tile<float>::bytes((int)slots) + CellSmem::bytes((int)slots, gx * gy) > budget) { gx = (gx * 7 + 7) / 8; gy = (gy * 7 + 7) / 8; }
+      // clustered pass: the per-warp group counts [32 warps][cells] alias one CTA's tile slice -> at most 2048 cells
+      while (h->cluster > 1 && gx * gy > 2048) { gx = (gx * 7 + 7) / 8; gy = (gy * 7 + 7) / 8; }
     }
-    if (gx >= 1 && gy >= 1 && (cfg->neighbor_search == EVAC_SEARCH_CELLS || gx * gy >= 16)) { h->cells_x = gx; h->cells_y = gy; h->cell_reach = reach; }
+    if (gx >= 1 && gy >= 1 && (cfg->neighbor_search == EVAC_SEARCH_CELLS || gx * gy >= 16 || h->cluster > 1)) { h->cells_x = gx; h->cells_y = gy; h->cell_reach = reach; }
     // paired walk (two adjacent sorted slots per thread share one window): pays when neighbouring slots usually share a cell.
     // Measured on B200, 20 steps after 0 / 64 / 300 warm-up steps: 256 x 4096 (2.7 per cell) 144 / 177 / 271 -> 129 / 167 / 265 us,
     // 1024 x 1000 109 -> 107 us, 2048 x 256 (0.17 per cell) 58 -> 63 us  => on from half a pedestrian per cell

@@ -23,6 +23,7 @@
 // slots are parked far away with a zero direction.  Nothing here is a dense contraction, so the
 // tensor cores are not used (BASELINE.json north_star).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -736,7 +737,11 @@ __device__ __forceinline__ void random_layout(uint64_t seed, uint32_t env, uint3
 // PPT pedestrians per thread (pedestrian i = k*THREADS + tid).  N <= 64 runs as ONE WARP per
 // environment (THREADS = 32, PPT = 2): no block barrier, reductions are pure REDUX / shuffles, and
 // the moving pedestrians are compacted (ballot + popc) so the pairwise pass only visits them.
-template <typename real, int THREADS, int PPT>  // @region load
+#include "evac_cluster.cuh"
+
+// CL > 1: ONE environment per thread-block cluster of CL CTAs (evac_cluster.cuh) -- CTA r owns pedestrians
+// [r * SLOTS, (r + 1) * SLOTS); float32 + cell list only; per-environment scalars are written by CTA 0.
+template <typename real, int THREADS, int PPT, int CL = 1>  // @region load
 __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 ? 16 : 1))) evac_step_kernel(const __grid_constant__ KArgs<real> a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int SLOTS = THREADS * PPT;
@@ -745,16 +750,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
   using real2 = typename vec2<real>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ RedScratch<WARPS> red_a, red_b;
+  __shared__ double cl_slot[8];  // CL > 1: this CTA's partial sums, read by the other CTAs of the cluster
+  int rank_cta = 0;
+  if constexpr (CL > 1) rank_cta = (int)cg::this_cluster().block_rank();
+  const int base_i = rank_cta * SLOTS;  // first pedestrian of this CTA
   Tile<real> tile(smem_raw, SLOTS);
   bool use_cells = false;  // CTA-uniform: cell-list neighbour search instead of the brute-force tiled pass
   if constexpr (!COMPACT && !F64) use_cells = a.cells_x > 0;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool lead = tid == 0 && rank_cta == 0;  // writes the per-environment scalars
   const int N = a.N;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const float noise_c = (float)a.noise_coef;
 
-  for (int e = blockIdx.x; e < a.E; e += gridDim.x) {
+  for (int e = blockIdx.x / CL; e < a.E; e += gridDim.x / CL) {
     // ---------------- load state (coalesced real2 per thread)
     real2* __restrict__ pos_e = a.pos + (size_t)e * N;
     real2* __restrict__ dir_e = a.dir + (size_t)e * N;
@@ -763,7 +773,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
     int st[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-      const int i = k * THREADS + tid;
+      const int i = base_i + k * THREADS + tid;
       px[k] = py[k] = dx[k] = dy[k] = (real)0;
       st[k] = ST_NONE;
       if (i < N) {
@@ -873,7 +883,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       if constexpr (!COMPACT && !F64) {
         if (use_cells) {
           const CellSmem cs(smem_raw + Tile<real>::bytes(SLOTS), SLOTS, a.cells_x * a.cells_y);
-          cell_list_pass<THREADS, PPT>(tile, cs, a, px, py, ux, uy, efv, st, sx, sy);
+          if constexpr (CL > 1) {
+            const ClusterSmem xs(smem_raw + Tile<real>::bytes(SLOTS) + CellSmem::bytes(SLOTS, a.cells_x * a.cells_y), a.cells_x * a.cells_y);
+            cell_list_pass_cluster<THREADS, PPT, CL>(tile, cs, xs, a, px, py, ux, uy, efv, st, sx, sy);
+          } else {
+            cell_list_pass<THREADS, PPT>(tile, cs, a, px, py, ux, uy, efv, st, sx, sy);
+          }
         }
       }
       if (use_cells) {
@@ -891,7 +906,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       const real e_adx = (real)__fmul_rn(a.enslaving_f, ad.x), e_ady = (real)__fmul_rn(a.enslaving_f, ad.y);
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
-        const int i = k * THREADS + tid;
+        const int i = base_i + k * THREADS + tid;
         const int so = st[k];
         const bool fv = (unsigned)(so - ST_VISCEK) <= (unsigned)(ST_FOLLOWER - ST_VISCEK);
         if (fv) {
@@ -958,8 +973,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
           for (int w = 0; w < WARPS; ++w) { q0 += red_a.i[w][0]; q1 += red_a.i[w][1]; q2 += red_a.i[w][2]; sd += red_a.f[w][0]; }
         }
       }
-      const int K_exit = q0 & 0xffff, K_fol = q0 >> 16, N_esc = q1 & 0xffff, N_exi = q1 >> 16, N_fol = q2;
-      if (a.status_counts != nullptr && tid == 0) {
+      int K_exit = q0 & 0xffff, K_fol = q0 >> 16, N_esc = q1 & 0xffff, N_exi = q1 >> 16, N_fol = q2;
+      if constexpr (CL > 1) {  // sums over the CTAs of the cluster, in rank order (same bits in every CTA)
+        double v[6] = {(double)K_exit, (double)K_fol, (double)N_esc, (double)N_exi, (double)N_fol, sd};
+        cluster_sum<CL, 6>(cl_slot, v);
+        K_exit = (int)v[0]; K_fol = (int)v[1]; N_esc = (int)v[2]; N_exi = (int)v[3]; N_fol = (int)v[4]; sd = v[5];
+      }
+      if (a.status_counts != nullptr && lead) {
         const ushort4 c4 = make_ushort4((unsigned short)N_esc, (unsigned short)N_exi, (unsigned short)N_fol, (unsigned short)(N - N_esc - N_exi - N_fol));
         reinterpret_cast<ushort4*>(a.status_counts)[(size_t)s * a.E + e] = c4;
       }
@@ -978,7 +998,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
       acc_r += (double)reward; acc_i += (double)intrinsic; acc_s += (double)r_status;
       // ---------------- same-step auto-reset  // @region reset
       if (a.auto_reset && (terminated || truncated)) {
-        if (tid == 0) {  // the logging dict of env.py:115-125
+        if (lead) {  // the logging dict of env.py:115-125
           if (!acc_reset) { acc_r += a.acc[3 * (size_t)e]; acc_i += a.acc[3 * (size_t)e + 1]; acc_s += a.acc[3 * (size_t)e + 2]; }
           float* es = a.ep_stats + (size_t)e * NUM_EPISODE_STATS;
           const float v[NUM_EPISODE_STATS] = {(float)acc_i, (float)acc_s, (float)acc_r, (float)now, (float)N_esc, (float)N_exi,
@@ -993,7 +1013,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         ap = make_float2(0.f, 0.f); ad = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
-          const int i = k * THREADS + tid;
+          const int i = base_i + k * THREADS + tid;
           if (i < N) {
             random_layout<real>(a.seed, env_g, (uint32_t)episode, (uint32_t)i, px[k], py[k], dx[k], dy[k]);
             real d2e;
@@ -1021,12 +1041,17 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) { nf += red_b.i[w][0]; wx += red_b.f[w][0]; wy += red_b.f[w][1]; }
           }
-          if (tid == 0) store_grav_obs<real>(row, ap.x, ap.y, (real)wx, (real)wy, nf, a);
+          if constexpr (CL > 1) {
+            double v[3] = {(double)nf, wx, wy};
+            cluster_sum<CL, 3>(cl_slot, v);
+            nf = (int)v[0]; wx = v[1]; wy = v[2];
+          }
+          if (lead) store_grav_obs<real>(row, ap.x, ap.y, (real)wx, (real)wy, nf, a);
         } else {
-          if (tid == 0) store_head_obs<real>(row, ap.x, ap.y, a);
+          if (lead) store_head_obs<real>(row, ap.x, ap.y, a);
 #pragma unroll
           for (int k = 0; k < PPT; ++k) {
-            const int i = k * THREADS + tid;
+            const int i = base_i + k * THREADS + tid;
             if (i < N) store_ped_obs<real>(row, i, N, px[k], py[k], st[k], ap.x, ap.y, a);
           }
         }
@@ -1036,7 +1061,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
     // ---------------- write back  // @region writeback
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-      const int i = k * THREADS + tid;
+      const int i = base_i + k * THREADS + tid;
       if (i < N) {
         real2 p, d;
         p.x = px[k]; p.y = py[k]; d.x = dx[k]; d.y = dy[k];
@@ -1045,7 +1070,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         st_e[i] = (uint8_t)st[k];
       }
     }
-    if (tid == 0) {
+    if (lead) {
       a.agent_pos[e] = ap; a.agent_dir[e] = ad;
       a.now[e] = now; a.episode[e] = episode; a.overall[e] += steps_total;
       if (a.agent_kind == AGENT_WACUUM) a.agent_state[e] = wac_state;

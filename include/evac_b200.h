@@ -83,7 +83,7 @@ enum { EVAC_SEARCH_AUTO = 0, EVAC_SEARCH_BRUTE = 1, EVAC_SEARCH_CELLS = 2 };
  * + SwitchDistances (distances.py:17-21).  Field names follow the reference. */
 typedef struct EvacConfig {
   int32_t abi_version;            /* must be EVAC_ABI_VERSION */
-  int32_t number_of_pedestrians;  /* N, 1 .. 8192 (fp64 parity mode: 1 .. 4096) */
+  int32_t number_of_pedestrians;  /* N, 1 .. 32768 (all-pairs search: 1 .. 8192; fp64 parity mode: 1 .. 4096) */
   double width, height;           /* arena half-extents */
   double step_size;
   double noise_coef;

@@ -325,23 +325,81 @@ def test_cell_list_paired_walk_is_bit_identical_to_the_single_slot_walk(n, width
 
 
 def test_pedestrian_count_limits():
-    """1 .. 8192 pedestrians per environment in float32 (the sorted tile + cell list of one environment must fit one SM's
-    shared memory), 1 .. 4096 in the fp64 parity mode; anything else fails loudly at creation."""
+    """1 .. 32768 pedestrians per environment in float32 with the cell list (one CTA up to 4096, a cluster of 2 / 4 / 8 CTAs
+    above), 1 .. 8192 with the all-pairs search, 1 .. 4096 in the fp64 parity mode; anything else fails loudly at creation."""
     import evacuation_b200 as eb
 
     wrap = eb.EnvWrappersConfig(positions="rel", statuses="ohe", type="Box")
-    with pytest.raises(ValueError, match="8192"):
-        eb.setup_env(eb.EnvConfig(number_of_pedestrians=8193), wrap, num_envs=2, batched=True).reset()
+    with pytest.raises(ValueError, match="32768"):
+        eb.setup_env(eb.EnvConfig(number_of_pedestrians=32769), wrap, num_envs=2, batched=True).reset()
+    with pytest.raises(ValueError, match="all-pairs"):
+        eb.setup_env(eb.EnvConfig(number_of_pedestrians=9000), wrap, num_envs=2, batched=True, neighbor_search="brute").reset()
     with pytest.raises(ValueError, match="fp64"):
         eb.setup_env(eb.EnvConfig(number_of_pedestrians=5000), wrap, num_envs=2, batched=True, precision="fp64").reset()
-    env = eb.setup_env(eb.EnvConfig(number_of_pedestrians=8192), wrap, num_envs=2, batched=True)
-    obs, _ = env.reset()
-    assert tuple(obs.shape) == (2, 8194, 6)
-    obs, r, term, trunc, _ = env.step(torch.zeros((2, 2), device="cuda") + 0.5)
-    assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(r).all())
-    st = env.unwrapped.get_state()
-    assert float(st["positions"].abs().max()) <= 1.0
-    env.unwrapped.close()
+    for n in (8192, 32768):
+        env = eb.setup_env(eb.EnvConfig(number_of_pedestrians=n), wrap, num_envs=2, batched=True, auto_reset=True)
+        obs, _ = env.reset()
+        assert tuple(obs.shape) == (2, n + 2, 6)
+        for _ in range(3):
+            obs, r, term, trunc, _ = env.step(torch.zeros((2, 2), device="cuda") + 0.5)
+        assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(r).all())
+        st = env.unwrapped.get_state()
+        assert float(st["positions"].abs().max()) <= 1.0
+        # statuses are a pure function of (position, agent position) [statuses.py:29-48]
+        exp = T.compute_statuses(st["positions"][0].double().cpu().numpy(), st["agent_position"][0].cpu().numpy(), np.array([0.0, -1.0]))[0]
+        assert (exp != st["statuses"][0].cpu().numpy()).mean() < 1e-3  # float32 vs float64 compares right at a threshold
+        env.unwrapped.close()
+
+
+@pytest.mark.parametrize("n,vision", [(8192, 0.1), (5000, 0.1), (8192, 0.02), (700, 0.1)])
+def test_cluster_pass_is_bit_identical_across_cluster_sizes(n, vision, monkeypatch):
+    """Crowds above 4096 pedestrians run one environment per thread-block cluster (evac_cluster.cuh): the sorted source tile
+    is distributed over the CTAs' shared memory and sorted by (cell, pedestrian index) exactly like the one-CTA pass, so the
+    one-CTA kernel (1024 x 8, EVAC_CLUSTER=1; itself checked against the all-pairs search) and clusters of 2, 4 and 8 CTAs
+    must produce the same state bit for bit over a free-running rollout with auto-reset, a dense cluster of pedestrians
+    included (rewards / gravity observations: sums over all pedestrians, identical between cluster sizes)."""
+    import evacuation_b200 as eb
+
+    monkeypatch.setattr(eb.SwitchDistances, "to_pedestrian", vision)
+    E, steps = 3, 8
+    env_kw = dict(number_of_pedestrians=n, is_new_exiting_reward=True, intrinsic_reward_coef=0.3, enslaving_degree=0.6, noise_coef=0.4,
+                  max_timesteps=5)
+    rs = np.random.RandomState(3 + n)
+    pos = rs.uniform(-1, 1, (E, n, 2))
+    pos[1, : n // 2] = np.array([0.55, 0.6]) + rs.normal(0, 0.04, (n // 2, 2))
+    pos = np.clip(pos, -1, 1)
+    ang = rs.uniform(0, 2 * np.pi, (E, n))
+    dirs = np.stack([np.cos(ang), np.sin(ang)], axis=-1)
+    actions = rs.uniform(-1, 1, (steps, E, 2)).astype(np.float32)
+    out = {}
+    for wrap in (dict(positions="rel", statuses="ohe", type="Box"), dict(positions="grav", alpha=3)):
+        for cl in ("1", "2", "4", "8"):
+            monkeypatch.setenv("EVAC_CLUSTER", cl)
+            env = eb.setup_env(eb.EnvConfig(wandb_enabled=False, **env_kw), eb.EnvWrappersConfig(**wrap), num_envs=E, batched=True, auto_reset=True)
+            u = env.unwrapped
+            u.reset()
+            u.set_state(positions=pos, directions=dirs, agent_position=np.zeros((E, 2), np.float32), agent_direction=np.zeros((E, 2), np.float32),
+                        now=np.zeros(E, np.int32))
+            rew, obs_all = [], []
+            for s in range(steps):  # the episodes are truncated at step 5 -> same-step auto-reset inside the rollout
+                obs, r, _, trunc, _ = env.step(torch.as_tensor(actions[s]))
+                rew.append(r.cpu().numpy().copy())
+                obs_all.append(_flat(obs, E).copy())
+            st = u.get_state()
+            out[cl] = dict(pos=st["positions"].cpu().numpy(), dir=st["directions"].cpu().numpy(), st=st["statuses"].cpu().numpy(),
+                           rew=np.array(rew), obs=np.array(obs_all))
+            u.close()
+        for cl in ("4", "8"):  # cluster sizes among themselves: every bit (the per-CTA partial sums are the same ones)
+            for k in ("pos", "dir", "st", "rew", "obs"):
+                assert np.array_equal(out["2"][k], out[cl][k], equal_nan=True), (wrap, cl, k)
+        if vision == 0.02:  # the clustered pass caps the grid at 2048 cells: other cells, other float32 summation order
+            assert np.abs(out["1"]["pos"] - out["2"]["pos"]).max() <= 5e-4 and (np.abs(out["1"]["pos"] - out["2"]["pos"]) <= 1e-6).mean() >= 0.999
+            assert (out["1"]["st"] != out["2"]["st"]).sum() <= 2
+            continue
+        for k in ("pos", "dir", "st"):  # against the one-CTA kernel: the state bit for bit ...
+            assert np.array_equal(out["1"][k], out["2"][k], equal_nan=True), (wrap, k)
+        for k in ("rew", "obs"):  # ... sums over ALL pedestrians (intrinsic reward, gravity observation) group the float32 partials differently
+            np.testing.assert_allclose(out["2"][k], out["1"][k], rtol=2e-6, atol=1e-6, err_msg=str((wrap, k)))
 
 
 def test_cell_list_nan_poisoning_matches_all_pairs():
@@ -544,7 +602,7 @@ def test_error_behaviour_matches_reference():
     with pytest.raises(AssertionError):  # wrappers/config.py:42-44
         eb.EnvWrappersConfig(num_obs_stacks=2)
     with pytest.raises(ValueError):
-        eb.EvacuationEnv(eb.EnvConfig(number_of_pedestrians=5000)).reset()
+        eb.EvacuationEnv(eb.EnvConfig(number_of_pedestrians=40000)).reset()
     env = eb.setup_env(eb.EnvConfig, eb.EnvWrappersConfig)  # README.md:72 passes the classes
     obs, _ = env.reset()
     assert set(obs) == {"agent_position", "pedestrians_positions", "exit_position"}

@@ -40,6 +40,19 @@ __device__ __forceinline__ void owner_of_pair(int pair, int& owner, int& local) 
   local = pair - owner * (SLOTS / 2);
 }
 
+// shared::cluster addressing of the walk: one MAPA per segment, then LDS-like 128-bit loads from the owning CTA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, int cta_rank) {
+  uint32_t r;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 template <int THREADS, int PPT, int CL, typename A>
 __device__ __forceinline__ void cell_list_pass_cluster(const Tile<float>& tile, const CellSmem& cs, const ClusterSmem& xs, const A& a,
                                                        const float (&px)[PPT], const float (&py)[PPT], const float (&ux)[PPT],
@@ -208,12 +221,15 @@ __device__ __forceinline__ void cell_list_pass_cluster(const Tile<float>& tile, 
         int owner, lp;
         owner_of_pair<SLOTS, CL>(j, owner, lp);
         const int seg_end = owner == CL - 1 ? je : min(je, (owner + 1) * (SLOTS / 2));
-        const float4* __restrict__ P = cluster.map_shared_rank(tile.P2 + lp, owner);
-        const float4* __restrict__ U = cluster.map_shared_rank(tile.U2 + lp, owner);
+        const uint32_t pa = mapa_u32(smem_u32(tile.P2 + lp), owner);
+        const uint32_t ua = pa + (uint32_t)((SLOTS / 2 + 1) * sizeof(float4));  // U2 = P2 + SLOTS / 2 + 1 in every CTA
         const int n = seg_end - j;
+        // software pipeline: the next slot pair is in flight while this one is evaluated (the look-ahead of the last
+        // iteration reads the spare entry behind the slice / the first U2 entry: allocated, never used)
+        float4 p = ld_cluster_f4(pa), u = ld_cluster_f4(ua);
 #pragma unroll 2
         for (int q = 0; q < n; ++q) {
-          const float4 p = P[q], u = U[q];
+          const float4 pn = ld_cluster_f4(pa + 16u * (uint32_t)(q + 1)), un = ld_cluster_f4(ua + 16u * (uint32_t)(q + 1));
           const float2 sxp = make_float2(p.x, p.y), syp = make_float2(p.z, p.w), sux = make_float2(u.x, u.y), suy = make_float2(u.z, u.w);
           {
             const float2 dx = __fadd2_rn(sxp, nx0), dy = __fadd2_rn(syp, ny0);
@@ -231,6 +247,8 @@ __device__ __forceinline__ void cell_list_pass_cluster(const Tile<float>& tile, 
             ax1 = __ffma2_rn(w, sux, ax1);
             ay1 = __ffma2_rn(w, suy, ay1);
           }
+          p = pn;
+          u = un;
         }
         j = seg_end;
       }

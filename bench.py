@@ -284,8 +284,9 @@ def run_ours(args):
     graph_a.replay()  # untimed: graph upload + one more pass over every set
     barrier()
     sampler.start()
-    # device head start: the GPU spins while the host submits the K-node graph launch, so the event pair brackets device
-    # execution only (the host-side launch of a large graph takes a few hundred microseconds before its first node runs)
+    # device head start: the GPU spins while the host submits the K-node graph launch, so that a host thread that is briefly
+    # descheduled (N ranks + samplers share the box's cores) cannot leave a gap inside the event pair (A/B on an idle
+    # host: no difference)
     if not os.environ.get("EVAC_BENCH_NO_HEADSTART"):
         torch.cuda._sleep(int((1e-3 + 1e-6 * K) * 1.9e9))
     e0.record()
@@ -454,6 +455,7 @@ def other_workloads(dev):
     out["c3_grav_4096x60"] = rollout_us(dict(number_of_pedestrians=60, enslaving_degree=0.5, noise_coef=0.5), dict(positions="grav", alpha=3), 4096, 200)
     out["c4_large_crowd_256x4096_cells"] = rollout_us(dict(number_of_pedestrians=4096), WRAP_KW, 256, 20)
     out["c4_large_crowd_256x4096_all_pairs"] = rollout_us(dict(number_of_pedestrians=4096), WRAP_KW, 256, 4, neighbor_search="brute")
+    out["large_crowd_32x32768_cluster"] = rollout_us(dict(number_of_pedestrians=32768), WRAP_KW, 32, 8)  # one env per 8-CTA cluster
     out["c5_env_only_65536x60"] = rollout_us(ENV_KW, WRAP_KW, 65536, 100)
     # config 5, one rank's share of the 8-GPU job (65536 / 8 envs) with the policy in the loop: the fused CUDA policy
     # (evac_policy_forward: embedding kernel + heads kernel, NormalizeObservation / ClipAction fused) and, beside it, the

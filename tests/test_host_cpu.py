@@ -177,3 +177,56 @@ def test_oracle_invariants_property():
         if term:
             break
     assert escaped_before.sum() > 0
+
+
+def test_header_is_plain_c_and_the_library_is_a_c_abi():
+    """include/evac_b200.h must compile as C99 (no torch / C++ types in the boundary) and a C program that only sees the
+    header must link against libevac_b200.so and reach the entry points that need no GPU."""
+    import shutil
+    import tempfile
+
+    from evacuation_b200 import build as b
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    header = os.path.join(ROOT, "include", "evac_b200.h")
+    res = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", header], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lib = b.build()
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "t.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include "evac_b200.h"\n'
+                    "int main(void) { EvacConfig c; if (evac_default_config(&c)) return 1;\n"
+                    '  printf("%d %d %g\\n", (int)evac_abi_version(), (int)c.number_of_pedestrians, c.to_exit);\n'
+                    "  return evac_default_config(0) == 0; }\n")
+        exe = os.path.join(tmp, "t")
+        res = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)],
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 0, run.stderr
+        version, n, to_exit = run.stdout.split()
+        assert int(n) == 10 and float(to_exit) == 0.4 and int(version) >= 1
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the reference algorithm on the host cores; runs without a GPU): exactly one JSON line on
+    stdout with the driver's keys, `impl`, a `cpu_baseline` describing the run and an `e2e` equal to the line's value."""
+    import json
+
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["steps"] == 3 and d["warmup"] == 1 and d["higher_is_better"] is True
+    assert d["unit"] == "pedestrian-steps/s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]

@@ -11,9 +11,9 @@
 //      Global slot = base[c] + rank: the tile is sorted by (cell, pedestrian index) exactly like the one-CTA pass,
 //      so every float32 sum has the same value as there.
 //   3. scatter of the source records into the tile slice of the CTA that owns the slot (DSMEM stores) -> cluster barrier
-//   4. paired walk (two adjacent sorted slots of one cell row per thread); the slot PAIRS are dealt out evenly over
-//      the CL CTAs, so a crowd that has collapsed into one corner is still walked by all of them; tile reads go to
-//      whichever CTA owns the slot pair; the result goes to the CTA that owns the pedestrian           -> cluster barrier
+//   4. paired walk (two adjacent sorted slots of one cell row per thread); the warps of the whole cluster draw chunks of
+//      slot pairs from one counter, so a crowd that has collapsed into one corner is still walked by all CTAs; tile reads
+//      go to whichever CTA owns the slot pair; the result goes to the CTA that owns the pedestrian     -> cluster barrier
 //   5. the owners read their results.
 // (textually included inside namespace evac, after cell_list_pass; <cooperative_groups.h> comes from evac_kernels.cuh)
 #pragma once
@@ -23,7 +23,7 @@ namespace cg = cooperative_groups;
 struct ClusterSmem {
   int* hist;    // [C + 1] own moving pedestrians per cell (read by the other CTAs)
   int* base;    // [C + 1] first global slot of this CTA's pedestrians of each cell
-  int* flags;   // [4]     [0] a source of this CTA has no direction (NaN poisoning)
+  int* flags;   // [4]     [0] a source of this CTA has no direction (NaN poisoning)  [1] (CTA 0) next slot pair of the walk
   static __host__ __device__ constexpr size_t bytes(int cells) { return 2 * (((size_t)cells + 1 + 3) & ~(size_t)3) * 4 + 16; }
   __device__ __forceinline__ ClusterSmem(unsigned char* p, int cells) {
     hist = reinterpret_cast<int*>(p);
@@ -66,7 +66,7 @@ __device__ __forceinline__ void cell_list_pass_cluster(const Tile<float>& tile, 
   // ---- 1. own histogram + rank inside (cell, CTA): lanes of one warp that share a cell find each other with MATCH.ANY,
   // the leader records the group size in cnt[warp][cell] (uint8; aliases the tile slice, which is only written in step 3)
   for (int c = tid; c <= C; c += THREADS) xs.hist[c] = 0;
-  if (tid == 0) xs.flags[0] = 0;
+  if (tid == 0) { xs.flags[0] = 0; xs.flags[1] = 0; }
   int cell[PPT], rank[PPT];
   bool nan_src = false;
   {
@@ -178,14 +178,22 @@ __device__ __forceinline__ void cell_list_pass_cluster(const Tile<float>& tile, 
     if (lane == 0 && a.cells_y == 64) cs.row_pairs[64] = run;
   }
   cluster.sync();  // the whole sorted tile is in place
-  // ---- 4. paired walk; this CTA takes an even share of the slot pairs
+  // ---- 4. paired walk.  The warps of the whole cluster draw chunks of 32 slot pairs from ONE counter (a DSMEM atomic on
+  // CTA 0's shared memory): a walk costs as much as its cells are crowded, so equal shares of slot pairs would leave the
+  // CTAs of a cluster waiting at the barrier for the one that drew the densest cells (ncu: `barrier` was the top stall).
+  // The result of a pair does not depend on who walks it.
   const float thr2 = a.thr2_ped;
   const int reach = a.cell_reach;
   const int n_pairs = cs.row_pairs[a.cells_y];
-  const int share = (n_pairs + CL - 1) / CL;
-  const int t_end = min((rank_cta + 1) * share, n_pairs);
+  int* const next_pair = cluster.map_shared_rank(xs.flags, 0) + 1;
 #pragma unroll 1
-  for (int t = rank_cta * share + tid; t < t_end; t += THREADS) {
+  for (;;) {
+    int tb = 0;
+    if (lane == 0) tb = atomicAdd(next_pair, 32);
+    tb = __shfl_sync(0xffffffffu, tb, 0);
+    if (tb >= n_pairs) break;
+    const int t = tb + lane;
+    if (t < n_pairs) do {  // (`continue` below leaves this one-trip loop)
     int row = 0;
     {
       int hi_r = a.cells_y;
@@ -256,6 +264,8 @@ __device__ __forceinline__ void cell_list_pass_cluster(const Tile<float>& tile, 
     }
     if (id0 & 0x8000) { const int i = id0 & 0x7fff; cluster.map_shared_rank(cs.res, i / SLOTS)[i % SLOTS] = make_float2(ax0.x + ax0.y, ay0.x + ay0.y); }
     if (id1 & 0x8000) { const int i = id1 & 0x7fff; cluster.map_shared_rank(cs.res, i / SLOTS)[i % SLOTS] = make_float2(ax1.x + ax1.y, ay1.x + ay1.y); }
+    } while (0);
+    __syncwarp();
   }
   cluster.sync();  // every result has reached its owner
   // ---- 5. back to the owners

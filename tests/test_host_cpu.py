@@ -230,3 +230,17 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bind_host_to_device_never_raises():
+    """The NUMA helper is opt-in plumbing for the host face: without NVML (this container) or on a single-node host it
+    must report what it did and leave the process affinity usable."""
+    from evacuation_b200.distributed import bind_host_to_device
+
+    before = os.sched_getaffinity(0)
+    info = bind_host_to_device(0)
+    assert isinstance(info, dict) and "bound" in info
+    after = os.sched_getaffinity(0)
+    assert after and after <= before
+    if not info["bound"]:
+        assert after == before and "reason" in info

@@ -8,9 +8,10 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+from . import build as _build
 from .build import LIB_PATH
 
-EVAC_ABI_VERSION = 3
+EVAC_ABI_VERSION = 4
 NUM_EPISODE_STATS = 9
 EPISODE_STAT_KEYS = (  # env.py:115-125
     "episode_intrinsic_reward", "episode_status_reward", "episode_reward", "episode_length",
@@ -70,6 +71,7 @@ _P = C.c_void_p
 SIGNATURES = {
     "evac_abi_version": (C.c_int32, []),
     "evac_last_error": (C.c_char_p, []),
+    "evac_build_id": (C.c_char_p, []),
     "evac_default_config": (C.c_int, [C.POINTER(EvacConfig)]),
     "evac_create": (C.c_int, [C.POINTER(EvacConfig), C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.POINTER(_P)]),
     "evac_destroy": (C.c_int, [_P]),
@@ -103,6 +105,11 @@ SIGNATURES = {
 _lib = None
 
 
+def build_id() -> str:
+    """Build id of the LOADED library (== evacuation_b200.build.source_hash() of the tree it was built from)."""
+    return load().evac_build_id().decode()
+
+
 class EvacNativeError(RuntimeError):
     pass
 
@@ -112,16 +119,26 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    want = _build.source_hash()
+    if _build.library_build_id() != want and not os.environ.get("EVAC_B200_LIB"):
+        # missing, or built from other sources than the tree holds (content hash, not mtime): rebuild or fail -- never run it
+        try:
+            _build.build(force=True)
+        except Exception as exc:
+            raise EvacNativeError(
+                f"{LIB_PATH} is missing or stale (build id {_build.library_build_id()} != source hash {want}) and could not be "
+                f"rebuilt: {exc}.  Build it with `python -m evacuation_b200.build`; evacuation_b200 has no CPU fallback.") from exc
     if not os.path.exists(LIB_PATH):
-        raise EvacNativeError(
-            f"{LIB_PATH} is missing: build it with `python -m evacuation_b200.build` "
-            "(or __graft_entry__.build()).  evacuation_b200 has no CPU fallback.")
+        raise EvacNativeError(f"{LIB_PATH} is missing: build it with `python -m evacuation_b200.build`.  evacuation_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype, fn.argtypes = res, args
     if lib.evac_abi_version() != EVAC_ABI_VERSION:
         raise EvacNativeError("libevac_b200.so ABI version mismatch; rebuild")
+    got = lib.evac_build_id().decode()
+    if got != want and not os.environ.get("EVAC_B200_LIB"):  # (EVAC_B200_LIB: an explicitly chosen kernel-variant build)
+        raise EvacNativeError(f"{LIB_PATH} was built from other sources (build id {got}, tree {want}); rebuild")
     _lib = lib
     return lib
 

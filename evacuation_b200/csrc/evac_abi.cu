@@ -264,6 +264,12 @@ static int set_device(const EvacHandle* h) {
 extern "C" {
 
 int32_t evac_abi_version(void) { return EVAC_ABI_VERSION; }
+// content hash of csrc/ + include/ at build time (evacuation_b200/build.py); the marker is also greppable in the binary
+#ifndef EVAC_BUILD_ID
+#define EVAC_BUILD_ID "unversioned-build"
+#endif
+static const char g_build_id[] = "EVAC_BUILD_ID=" EVAC_BUILD_ID;
+const char* evac_build_id(void) { return g_build_id + 14; }
 const char* evac_last_error(void) { return g_err; }
 
 int evac_default_config(EvacConfig* c) {

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define EVAC_ABI_VERSION 3
+#define EVAC_ABI_VERSION 4
 
 enum {
   EVAC_OK = 0,
@@ -108,6 +108,11 @@ typedef struct EvacConfig {
   int32_t precision;  /* EVAC_PREC_F32 (product) or EVAC_PREC_F64 (parity mode) */
   int32_t neighbor_search; /* EVAC_SEARCH_* */
 } EvacConfig;
+
+/* Content hash (16 hex digits) of the sources this library was built from: SHA-256 over every .cu / .cuh file of csrc/ and
+ * every .h file of include/ (evacuation_b200/build.py::source_hash).  The Python loader refuses a library whose id differs from the
+ * tree's, so tests and benchmarks cannot run a stale binary. */
+const char* evac_build_id(void);
 
 typedef struct EvacHandle EvacHandle;
 

@@ -1,10 +1,11 @@
 """Import shim that lets the UNMODIFIED reference (cinemere/evacuation, /root/reference) run
 in a container without gymnasium / matplotlib.
 
-TEST INFRASTRUCTURE ONLY.  This file is used by tests/golden/gen_golden.py (run in the
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  This file is used by tests/golden/gen_golden.py (run in the
 authoring container, where /root/reference is mounted) to produce the committed golden
-vectors.  Nothing in the product path imports it, and it is never used on the GPU box
-(/root/reference does not exist there).
+vectors, and by bench.py's CPU arm (`--impl reference`, `cpu_baseline`) to time the unmodified
+reference where it is reachable (/root/reference here; baseline/_ref on the GPU box).  Nothing in
+the product path imports it.
 
 It provides the tiny gymnasium surface the reference's env package touches
 (SURVEY.md appendix A): gymnasium.Env, gymnasium.ObservationWrapper, spaces.Box / spaces.Dict,
@@ -18,11 +19,23 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("EVAC_REFERENCE_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def find_reference_root():
+    """First of $EVAC_REFERENCE_ROOT, /root/reference (authoring container), <repo>/baseline/_ref (the pip --target install
+    made by oracle/install_reference.py; it travels to the GPU box) that holds the reference's `src/env` package."""
+    for cand in (os.environ.get("EVAC_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO_ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "src", "env", "env", "area.py")):
+            return cand
+    return None
+
+
+REFERENCE_ROOT = find_reference_root() or "/root/reference"
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "env"))
+    return find_reference_root() is not None
 
 
 class _Box:

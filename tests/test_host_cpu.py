@@ -39,6 +39,41 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert lib.evac_default_config(None) == -1 and b"NULL" in lib.evac_last_error()
 
 
+def test_build_id_pins_the_binary_to_the_sources(tmp_path, monkeypatch):
+    """Staleness is decided by content, not mtime: the library carries the SHA-256 of csrc/*.cu, csrc/*.cuh and
+    include/*.h; a change to ANY of those files (evac_cluster.cuh was once missing from the header list) makes
+    is_stale() true, and the loaded library reports the tree's hash."""
+    import glob
+    import shutil
+
+    from evacuation_b200 import _native as nat
+    from evacuation_b200 import build as b
+
+    b.build()
+    want = b.source_hash()
+    assert re.fullmatch(r"[0-9a-f]{16}", want)
+    assert b.library_build_id() == want and not b.is_stale()
+    assert nat.load().evac_build_id().decode() == want == nat.build_id()
+    tracked = {os.path.basename(p) for p in b.sources() + b.headers()}
+    on_disk = {os.path.basename(p) for pat in ("csrc/*.cu", "csrc/*.cuh") for p in glob.glob(os.path.join(ROOT, "evacuation_b200", pat))}
+    assert on_disk <= tracked and "evac_cluster.cuh" in tracked and "evac_b200.h" in tracked
+    # a scratch copy of the tree: appending one byte to each file in turn changes the hash (mtimes play no role)
+    csrc, inc = tmp_path / "csrc", tmp_path / "include"
+    shutil.copytree(b.CSRC, csrc, ignore=shutil.ignore_patterns("*.o"))
+    shutil.copytree(b.INCLUDE, inc)
+    monkeypatch.setattr(b, "CSRC", str(csrc))
+    monkeypatch.setattr(b, "INCLUDE", str(inc))
+    assert b.source_hash() == want and not b.is_stale()
+    for path in b.sources() + b.headers():
+        old = open(path, "rb").read()
+        with open(path, "ab") as f:
+            f.write(b"\n")
+        os.utime(path, (0, 0))  # an OLD mtime must not hide the change
+        assert b.source_hash() != want and b.is_stale(), path
+        open(path, "wb").write(old)
+    assert b.source_hash() == want and not b.is_stale()
+
+
 def test_cuda_library_contains_sm100a_packed_fp32_code():
     """The shipped .so carries sm_100a SASS with the packed FP32 pipe instructions of the pairwise pass."""
     from evacuation_b200 import build as b

@@ -67,10 +67,14 @@ __host__ __device__ __forceinline__ uint32_t evac_key32(uint64_t seed, uint32_t 
   return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ (episode * 0xBB67AE85u) ^ (stream * 0x85EBCA6Bu);
 }
 
-// Angular noise [area.py:124]: pedestrian i reads word (i >> 5) & 1 of block (i & 31) | (i >> 6) << 5 (block < 2048 for
-// N <= 4096), i.e. pedestrians i and i + 32 of every group of 64 share a block; counter = (block | now << 11, global env).
+// Angular noise [area.py:124]: pedestrian i reads word (i >> 5) & 1 of block (i & 31) | (i >> 6) << 5, i.e. pedestrians i and
+// i + 32 of every group of 64 share a block.  counter = ((block & 2047) | now << 11, global env): the low 11 block bits sit
+// next to the 21-bit step index; the upper block bits (block >= 2048 <=> pedestrian >= 4096, crowds up to 32 768) go into
+// the KEY through an odd multiplier -- for a fixed (env, episode, step) every block still owns its own (counter, key).
+// (They must not spill into the step field: block | now << 11 would alias pedestrian i + 4096 at step t with pedestrian i
+// at step t + 1.)
 __host__ __device__ __forceinline__ uint2 evac_noise_block(uint64_t seed, uint32_t env, uint32_t episode, uint32_t now, uint32_t block) {
-  return philox2x32_10(block | (now << 11), env, evac_key32(seed, STREAM_NOISE, episode));
+  return philox2x32_10((block & 2047u) | (now << 11), env, evac_key32(seed, STREAM_NOISE, episode) ^ ((block >> 11) * 0xC2B2AE35u));
 }
 __host__ __device__ __forceinline__ uint32_t evac_noise_block_of(uint32_t i) { return (i & 31u) | ((i >> 6) << 5); }
 __host__ __device__ __forceinline__ uint32_t evac_noise_word_of(uint32_t i) { return (i >> 5) & 1u; }

@@ -277,6 +277,13 @@ class EvacuationEnv:
         return self._obs_dim
 
     @property
+    def flat_observation(self) -> torch.Tensor:
+        """The [E, obs_dim] float32 device buffer the kernel writes: gymnasium `FlattenObservation` of the wrapped
+        observation (Dict keys in sorted order / Box rows row-major), valid after reset() and after every batched step()."""
+        self._handle()
+        return self._obs
+
+    @property
     def num_cells(self) -> int:
         """Cells of the neighbour-search grid (0 = all-pairs tiles)."""
         return int(nat.load().evac_num_cells(self._handle()))

@@ -6,14 +6,30 @@ import numpy as np
 
 
 class Box:
-    def __init__(self, low, high, shape=None, dtype=np.float32):
+    def __init__(self, low, high, shape=None, dtype=np.float32, seed=None):
         self.dtype = np.dtype(dtype)
         self.shape = tuple(shape) if shape is not None else tuple(np.shape(low))
         self.low = np.full(self.shape, low, dtype=self.dtype)
         self.high = np.full(self.shape, high, dtype=self.dtype)
+        self._np_random = None
+        if seed is not None:
+            self.seed(seed)
+
+    # Like gymnasium's spaces, a Box samples from ITS OWN generator -- never from the global `np.random` stream, which the
+    # single-env face (rng="numpy") consumes in the reference's order (pedestrians.py:17-18, area.py:124): an
+    # `action_space.sample()` between two steps (RandomAgent, random_agent.py:8-9) must not shift that stream.
+    @property
+    def np_random(self) -> np.random.Generator:
+        if self._np_random is None:
+            self.seed()
+        return self._np_random
+
+    def seed(self, seed=None):
+        self._np_random = np.random.default_rng(seed)
+        return [seed]
 
     def sample(self):
-        return np.random.uniform(self.low, self.high).astype(self.dtype)
+        return self.np_random.uniform(self.low, self.high).astype(self.dtype)
 
     def contains(self, x) -> bool:
         x = np.asarray(x)
@@ -29,6 +45,11 @@ class Dict(dict):
         if spaces is not None:
             self.update(spaces)
         self.update(kwargs)
+
+    def seed(self, seed=None):
+        for i, v in enumerate(self.values()):
+            v.seed(None if seed is None else seed + i)
+        return [seed]
 
     def sample(self):
         return {k: v.sample() for k, v in self.items()}

@@ -41,8 +41,9 @@ class EvacuationVectorEnv:
         if output not in ("numpy", "torch"):
             raise ValueError("output must be 'numpy' or 'torch'")
         self.output = output
+        # batched=True also for num_envs == 1 (the class default): torch tensors on the device, Philox streams, auto-reset
         self.env = setup_env(env_config, env_wrappers_config, num_envs=num_envs, device=device, seed=seed, auto_reset=True,
-                             env_index_offset=env_index_offset)
+                             env_index_offset=env_index_offset, batched=True)
         u = self.env.unwrapped
         self.num_envs, self.device, self.obs_dim = u.num_envs, u.device, u.obs_dim
         self.gamma = gamma
@@ -66,14 +67,16 @@ class EvacuationVectorEnv:
 
     def reset(self, seed=None, options=None):
         """Every sub-env's `reset()` through the wrapper chain: NormalizeObservation.reset also updates its estimate."""
-        obs, _ = self.env.reset(seed=seed)
-        return self._out(self.norm.observation(obs.reshape(self.num_envs, self.obs_dim)).float()), {}
+        self.env.reset(seed=seed)
+        return self._out(self.norm.observation(self.unwrapped.flat_observation).float()), {}
 
     def step(self, actions):
         act = torch.as_tensor(np.asarray(actions, dtype=np.float32) if not torch.is_tensor(actions) else actions)
         act = act.to(device=self.device, dtype=torch.float32).reshape(self.num_envs, 2).clamp(-1.0, 1.0).contiguous()  # ClipAction
-        obs, reward, term, trunc, _ = self.env.step(act)
-        obs_n = self.norm.observation(obs.reshape(self.num_envs, self.obs_dim))
+        _, reward, term, trunc, _ = self.env.step(act)
+        # FlattenObservation: the kernel's flat row IS the flattened observation for every wrapper configuration
+        # (Dict keys in sorted order, Box rows row-major) -- the structured Dict / Box view is not re-flattened here
+        obs_n = self.norm.observation(self.unwrapped.flat_observation)
         rew_n = self.norm.reward(reward, term)
         infos = {}
         done = term | trunc

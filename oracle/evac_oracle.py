@@ -133,6 +133,7 @@ class StepInfo:
     min_resultant: float = np.inf
     n_noise_used: int = 0
     fv_mask: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=bool))
+    pair_margin_rows: np.ndarray = field(default_factory=lambda: np.zeros(0))
 
 
 class OracleEnv:
@@ -157,6 +158,9 @@ class OracleEnv:
             raise NotImplementedError  # wrappers/config.py:80-81
         # RelativePosition.__init__ (wrappers.py:12-18): sqrt(low**2 + high**2) in float32
         self._hyp = np.sqrt(np.float32(-1) ** 2 + np.float32(1) ** 2).astype(np.float32)
+        # rows of the |fv| x |efv| distance matrix evaluated at once (None = all, like the reference); see _pedestrians_step
+        self.row_chunk = None
+        self.chunk_threads = 0  # > 0: row blocks evaluated by that many threads (same numbers; only for the big parity cases)
 
     # ------------------------------------------------------------------ state
     def get_state(self) -> dict:
@@ -244,15 +248,40 @@ class OracleEnv:
         with np.errstate(invalid="ignore", divide="ignore"):
             e_unit = (e_dirs.T / np.sqrt(e_dirs[:, 0] * e_dirs[:, 0] + e_dirs[:, 1] * e_dirs[:, 1])).T
 
-        dm = _pairwise_distance(pos[fv], pos[efv])
-        if dm.size:
+        # area.py:105-119.  One broadcast expression like the reference for ordinary sizes; for crowds whose |fv| x |efv|
+        # float64 matrix would not fit in memory (the > 8192-pedestrian parity cases) the SAME expressions are evaluated on
+        # blocks of rows -- every row's sums (a reduction along the contiguous axis) are the same numbers either way
+        # (tests/test_oracle_golden.py::test_row_chunked_alignment_is_bit_identical).
+        pos_fv, pos_efv = pos[fv], pos[efv]
+        chunk = self.row_chunk if self.row_chunk else max(1, pos_fv.shape[0])
+
+        def rows(r0):
+            dm = _pairwise_distance(pos_fv[r0:r0 + chunk], pos_efv)
+            gap = None
+            if dm.size:
+                with np.errstate(invalid="ignore"):
+                    gap = np.abs(dm - SWITCH_DISTANCE_TO_OTHER_PEDESTRIAN).min(axis=1)  # NaN rows stay NaN
+            inter = np.where(dm < SWITCH_DISTANCE_TO_OTHER_PEDESTRIAN, 1, 0)
+            n_inter = np.maximum(1, inter.sum(axis=1))
             with np.errstate(invalid="ignore"):
-                margins.append(float(np.nanmin(np.abs(dm - SWITCH_DISTANCE_TO_OTHER_PEDESTRIAN))))
-        inter = np.where(dm < SWITCH_DISTANCE_TO_OTHER_PEDESTRIAN, 1, 0)
-        n_inter = np.maximum(1, inter.sum(axis=1))
-        with np.errstate(invalid="ignore"):
-            mx = (inter * e_unit[:, 0]).sum(axis=1) / n_inter
-            my = (inter * e_unit[:, 1]).sum(axis=1) / n_inter
+                return ((inter * e_unit[:, 0]).sum(axis=1) / n_inter, (inter * e_unit[:, 1]).sum(axis=1) / n_inter, gap)
+
+        starts = list(range(0, pos_fv.shape[0], chunk)) if pos_fv.shape[0] else [0]
+        if self.chunk_threads and len(starts) > 1:  # NumPy releases the GIL inside its loops; the row blocks are independent
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(self.chunk_threads) as pool:
+                parts = list(pool.map(rows, starts))
+        else:
+            parts = [rows(r0) for r0 in starts]
+        mx, my = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+        gaps = [p[2] for p in parts if p[2] is not None]
+        if gaps:
+            row_gap = np.concatenate(gaps)
+            info.pair_margin_rows = row_gap  # per VISCEK/FOLLOWER pedestrian: distance of its closest pair to the vision radius
+            with np.errstate(invalid="ignore"):
+                if np.isfinite(row_gap).any():
+                    margins.append(float(np.nanmin(row_gap)))
         theta = np.arctan2(my, mx)
         if mx.size:
             with np.errstate(invalid="ignore"):

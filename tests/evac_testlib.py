@@ -103,10 +103,12 @@ def evac_key32(seed, stream, episode):
 
 def philox_noise(seed, env, episode, now, n, noise_coef):
     """Dense [n] float32 noise the kernels draw for (env, episode, step-in-episode `now`): pedestrian i reads word
-    (i >> 5) & 1 of Philox2x32 block (i & 31) | (i >> 6) << 5, counter (block | now << 11, env)."""
+    (i >> 5) & 1 of Philox2x32 block (i & 31) | (i >> 6) << 5, counter ((block & 2047) | now << 11, env), the upper block
+    bits (pedestrians >= 4096) folded into the key."""
     i = np.arange(n, dtype=np.int64)
     block = (i & 31) | ((i >> 6) << 5)
-    r = philox2x32_10(block | (now << 11), env, evac_key32(seed, STREAM_NOISE, episode))
+    key = np.uint64(evac_key32(seed, STREAM_NOISE, episode)) ^ ((block >> 11).astype(np.uint64) * np.uint64(0xC2B2AE35) & np.uint64(0xFFFFFFFF))
+    r = philox2x32_10((block & 2047) | (now << 11), env, key)
     words = np.where(((i >> 5) & 1) == 1, r[1], r[0])
     return (u01(words) - np.float32(0.5)) * np.float32(noise_coef)
 

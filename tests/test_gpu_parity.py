@@ -138,13 +138,35 @@ def test_teacher_forced_one_step_parity(name):
     _assert_obs_close(case["wrap"], _flat(obs, steps), rec["obs"], same)
 
 
+def _record_summary(kind, name, summary):
+    """Per-case parity numbers -> gpurun_out/parity/<kind>__<name>.json (merged back by gpurun; the round's copy is
+    committed under profiles/): what the free-running comparison actually observed, not only that it stayed under a bound."""
+    import json
+
+    out = os.path.join(T.ROOT, "gpurun_out", "parity")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f"{kind}__{name}.json"), "w") as f:
+        json.dump(summary, f, indent=1, sort_keys=True)
+
+
+# free-running bars (north_star: 1e-5 relative over a 2000-step episode in fp32).  POSITIONS / REWARDS: strict 1e-5 on
+# every step.  DIRECTIONS (relative to step_size): 1e-5 except on the entries whose heading is ill-conditioned on that step
+# (|mean of the neighbour unit vectors| small: a float32 rounding of ~6e-8 in the sum turns into 6e-8 / |mean| of angle) --
+# those may reach FREE_DIR_CAP and must stay a small fraction of all entries.  Values set from the recorded summaries
+# (profiles/r02*/parity/): see DESIGN.md section 4.
+FREE_POS_RTOL = 1e-5
+FREE_DIR_CAP = 2e-3
+FREE_DIR_FRAC = 2e-3
+
+
 @pytest.mark.parametrize("name", ["c2_rel_ohe_box_seed0", "c2_rel_ohe_box_seed3", "c3_grav_a3", "c1_default_seed0", "c1_default_seed1",
                                   "n10_abs_cat_dict", "n33_rel_no_dict", "n60_box_1p5x0p8", "n3_escape_all"])
 def test_free_running_episode_parity(name):
-    """Free-running episode (up to 2000 steps): the kernel carries its own float32 state; the oracle its
-    float64 state; same actions and injected noise.  Statuses / flags must agree bit-exactly at every
-    step whose oracle margin exceeds the accumulated float32 drift; at a near-threshold step a
-    disagreement is tolerated, counted, and the kernel state is re-synchronised from the oracle."""
+    """Free-running episode (up to 2000 steps): the kernel carries its own float32 state, the oracle its float64 state;
+    same actions and injected noise; the kernel state is NEVER re-synchronised because of numerical error -- only when a
+    thresholded decision flips at a step whose oracle margin is below the accumulated float32 drift (a status / neighbour
+    set that legitimately differs; at most 3 per episode, each asserted to be a near-threshold step).  Everything observed
+    is recorded (resyncs, ill-conditioned steps, worst errors and when) in gpurun_out/parity/."""
     case, z = T.load_golden(name)
     rec = _run_oracle_episode(case, z)
     steps = len(rec["reward"])
@@ -154,36 +176,52 @@ def test_free_running_episode_parity(name):
     u.set_state(positions=rec["pre_pos"][0], directions=rec["pre_dir"][0], statuses=rec["pre_st"][0],
                 agent_position=rec["pre_apos"][0], agent_direction=rec["pre_adir"][0], now=np.zeros(1, np.int32))
     step_size = case["env"].get("step_size", 0.01)
-    resyncs, illcond, worst_pos, worst_dir, worst_rew = 0, 0, 0.0, 0.0, 0.0
     actions = torch.as_tensor(rec["actions"]).cuda()
     noise = torch.as_tensor(rec["noise"]).cuda()
+    pos_t, dir_t, st_t, rew_t, term_t, trunc_t = [], [], [], [], [], []
+    resync_steps = []
     for t in range(steps):
         obs, reward, term, trunc, _ = env.step(actions[t:t + 1], noise=noise[t:t + 1])
         st = u.get_state()
         got_st = st["statuses"][0].cpu().numpy()
+        pos_t.append(st["positions"][0].cpu().numpy()); dir_t.append(st["directions"][0].cpu().numpy()); st_t.append(got_st)
+        rew_t.append(float(reward[0])); term_t.append(bool(term[0])); trunc_t.append(bool(trunc[0]))
         if not np.array_equal(got_st, rec["post_st"][t]) or bool(term[0]) != bool(rec["term"][t]):
             assert rec["margin"][t] < 2e-5, f"step {t}: status mismatch with oracle margin {rec['margin'][t]:.3e}"
-            resyncs += 1
+            resync_steps.append(t)
             u.set_state(positions=rec["post_pos"][t], directions=rec["post_dir"][t], statuses=rec["post_st"][t],
                         agent_position=rec["post_apos"][t])
-            continue
-        assert bool(trunc[0]) == bool(rec["trunc"][t])
-        alive = (rec["post_st"][t] != 4)[:, None]
-        if rec["resultant"][t] < 0.02:
-            # ill-conditioned heading (neighbour unit vectors nearly cancel): float32 cannot resolve the argument of
-            # the sum to 1e-5 of a step; hold the kernel to 1e-3 of a step on this step and re-synchronise
-            illcond += 1
-            _assert_close(f"positions@{t}", st["positions"][0].cpu().numpy(), rec["post_pos"][t], rtol=1e-4)
-            u.set_state(positions=rec["post_pos"][t], directions=rec["post_dir"][t], statuses=rec["post_st"][t],
-                        agent_position=rec["post_apos"][t])
-            continue
-        worst_pos = max(worst_pos, _assert_close(f"positions@{t}", st["positions"][0].cpu().numpy(), rec["post_pos"][t]))
-        worst_dir = max(worst_dir, _assert_close(f"directions@{t}", st["directions"][0].cpu().numpy() * alive, rec["post_dir"][t] * alive, scale=step_size,
-                                                 ill_conditioned=0.05, cap=100.0))
-        worst_rew = max(worst_rew, _assert_close(f"reward@{t}", reward.cpu().numpy(), rec["reward"][t:t + 1]))
-    assert resyncs <= 3, f"{resyncs} near-threshold re-synchronisations in {steps} steps"
-    assert illcond <= max(3, steps // 25), f"{illcond} ill-conditioned-heading steps in {steps}"
-    print(f"[{name}] steps={steps} resyncs={resyncs} illcond={illcond} max rel err pos={worst_pos:.2e} dir={worst_dir:.2e} reward={worst_rew:.2e}")
+    pos_t, dir_t, st_t = np.array(pos_t, dtype=np.float64), np.array(dir_t, dtype=np.float64), np.array(st_t)
+    ok = np.ones(steps, dtype=bool)
+    ok[resync_steps] = False
+    assert np.array_equal(np.array(trunc_t), rec["trunc"].astype(bool))
+    assert np.array_equal(st_t[ok], rec["post_st"][ok]) and np.array_equal(np.array(term_t)[ok], rec["term"][ok].astype(bool))
+    # errors per step (NaN patterns must agree; none of these goldens goes NaN)
+    pos_err = np.abs(pos_t - rec["post_pos"]) / np.maximum(np.abs(rec["post_pos"]), 1.0)
+    alive = (rec["post_st"] != 4)[..., None]
+    dir_err = np.abs(dir_t * alive - rec["post_dir"] * alive) / np.maximum(np.abs(rec["post_dir"] * alive), step_size)
+    rew_err = np.abs(np.array(rew_t) - rec["reward"]) / np.maximum(np.abs(rec["reward"]), 1.0)
+    assert np.isfinite(pos_err).all() and np.isfinite(dir_err).all()
+    pos_step, dir_step = pos_err.reshape(steps, -1).max(axis=1), dir_err.reshape(steps, -1).max(axis=1)
+    pos_step[~ok] = 0.0; dir_step[~ok] = 0.0; rew_err[~ok] = 0.0
+    illcond = rec["resultant"] < 0.02
+    marks = [m for m in (100, 500, 1000, 1500, 2000) if m <= steps]
+    summary = dict(
+        case=name, steps=int(steps), status_resyncs=len(resync_steps), resync_steps=[int(x) for x in resync_steps],
+        resync_margins=[float(rec["margin"][x]) for x in resync_steps], illcond_steps=int(illcond.sum()),
+        worst_pos=float(pos_step.max()), worst_pos_step=int(pos_step.argmax()), worst_dir=float(dir_step.max()), worst_dir_step=int(dir_step.argmax()),
+        worst_dir_well_conditioned=float(dir_step[~illcond].max(initial=0.0)), worst_reward=float(rew_err.max()),
+        dir_entries_above_1e5=float((dir_err[ok] > 1e-5).mean()) if ok.any() else 0.0,
+        pos_steps_above_1e5=int((pos_step > 1e-5).sum()),
+        worst_pos_up_to={str(m): float(pos_step[:m].max()) for m in marks}, worst_dir_up_to={str(m): float(dir_step[:m].max()) for m in marks},
+        bars=dict(pos=FREE_POS_RTOL, dir_cap=FREE_DIR_CAP, dir_frac=FREE_DIR_FRAC, max_status_resyncs=3))
+    _record_summary("free_running", name, summary)
+    print(f"[{name}] {summary}")
+    assert len(resync_steps) <= 3, f"{len(resync_steps)} near-threshold re-synchronisations in {steps} steps"
+    assert pos_step.max() <= FREE_POS_RTOL, f"positions: max rel err {pos_step.max():.3e} at step {pos_step.argmax()}"
+    assert rew_err.max() <= FREE_POS_RTOL, f"reward: max rel err {rew_err.max():.3e}"
+    assert dir_step.max() <= FREE_DIR_CAP, f"directions: max err {dir_step.max():.3e} of a step at step {dir_step.argmax()}"
+    assert summary["dir_entries_above_1e5"] <= FREE_DIR_FRAC, f"directions: {summary['dir_entries_above_1e5']:.2e} of the entries exceed 1e-5"
 
 
 @pytest.mark.parametrize("n,num_envs,steps", [(1, 7, 3), (2, 5, 3), (31, 3, 3), (32, 3, 3), (64, 4, 3), (65, 3, 2), (128, 2, 2), (129, 2, 2),
@@ -400,6 +438,79 @@ def test_cluster_pass_is_bit_identical_across_cluster_sizes(n, vision, monkeypat
             assert np.array_equal(out["1"][k], out["2"][k], equal_nan=True), (wrap, k)
         for k in ("rew", "obs"):  # ... sums over ALL pedestrians (intrinsic reward, gravity observation) group the float32 partials differently
             np.testing.assert_allclose(out["2"][k], out["1"][k], rtol=2e-6, atol=1e-6, err_msg=str((wrap, k)))
+
+
+@pytest.mark.parametrize("n,cluster", [(16384, "4"), (16384, "8"), (32768, "8"), (32768, "4")])
+def test_cluster_path_against_the_oracle(n, cluster, monkeypatch):
+    """Crowds above one SM's shared memory (evac_cluster.cuh, area.py:105-119 semantics) against the ORACLE itself, not only
+    against the one-CTA kernel: teacher-forced steps at 16 384 and 32 768 pedestrians, a uniform layout (env 0) and one
+    with half the crowd in a dense blob (env 1), cluster sizes 4 and 8.  The oracle evaluates the float64 distance matrix in
+    row blocks (same numbers, tests/test_oracle_golden.py::test_row_chunked_alignment_is_bit_identical).  With ~1e9 pairs
+    SOME pair always sits within 1e-8 of the vision radius, so the near-threshold protocol is applied per pedestrian.  Both
+    sides start every step from the SAME float32-representable state, so a pair test can only flip within ~1e-8 of the
+    radius (float32 rounding of dx, dy, d^2): a pedestrian whose own closest pair is within 1e-7 of the radius, or whose
+    status / wall distance is within 1e-6 of its threshold, is excluded (counted, < 3 % even inside the blob, where
+    every pedestrian has ~1000 neighbours); every other pedestrian must match -- statuses bit-exactly."""
+    import evacuation_b200 as eb
+
+    monkeypatch.setenv("EVAC_CLUSTER", cluster)
+    E, steps = 2, 2 if n <= 16384 else 1
+    env_kw = dict(number_of_pedestrians=n, is_new_exiting_reward=True, intrinsic_reward_coef=0.3, enslaving_degree=0.6, noise_coef=0.4)
+    wrap = dict(positions="rel", statuses="ohe", type="Box")
+    rs = np.random.RandomState(n + int(cluster))
+    env = _make_env(env_kw, wrap, E)
+    u = env.unwrapped
+    u.reset()
+    assert u.num_cells > 0
+    oracles = []
+    for e in range(E):
+        o = OracleEnv(OracleConfig(**env_kw, **wrap))
+        o.row_chunk, o.chunk_threads = 256, min(16, os.cpu_count() or 1)
+        np.random.seed(77 + e)
+        o.reset()
+        if e == 1:
+            o.positions[: n // 4] = np.clip(np.array([0.5, 0.45]) + rs.normal(0, 0.06, (n // 4, 2)), -1, 1)
+        o.agent_position = rs.uniform(-0.5, 0.5, 2).astype(np.float32)
+        o.statuses = T.compute_statuses(o.positions, o.agent_position, o.exit_position)[0]
+        oracles.append(o)
+    excluded = []
+    for s_ in range(steps):
+        for o in oracles:  # teacher forcing from a float32-representable state (what set_state hands the kernel)
+            o.positions = o.positions.astype(np.float32).astype(np.float64)
+            o.directions = o.directions.astype(np.float32).astype(np.float64)
+        u.set_state(positions=np.stack([o.positions for o in oracles]), directions=np.stack([o.directions for o in oracles]),
+                    statuses=np.stack([o.statuses for o in oracles]), agent_position=np.stack([o.agent_position for o in oracles]),
+                    agent_direction=np.stack([o.agent_direction for o in oracles]), now=np.array([o.now for o in oracles], np.int32))
+        actions = rs.uniform(-1, 1, (E, 2)).astype(np.float32)
+        noise = rs.uniform(-0.2, 0.2, (E, n)).astype(np.float32)
+        obs, reward, term, trunc, _ = env.step(torch.as_tensor(actions), noise=torch.as_tensor(noise))
+        st = u.get_state()
+        flat = _flat(obs, E).reshape(E, n + 2, 6)
+        for e, o in enumerate(oracles):
+            pre_st = o.statuses.copy()
+            oobs, r, tm, tr, info = o.step(actions[e].copy(), noise[e].astype(np.float64))
+            # per-pedestrian ambiguity: own closest pair vs the vision radius, status distances, wall distance
+            amb = np.zeros(n, dtype=bool)
+            amb[np.nonzero(info.fv_mask)[0][info.pair_margin_rows < 1e-7]] = True
+            d_ag = np.linalg.norm(o.positions - o.agent_position.astype(np.float64), axis=1)
+            d_ex = np.linalg.norm(o.positions - np.array([0.0, -1.0]), axis=1)
+            amb |= (np.abs(d_ag - 0.2) < MARGIN_TOL) | (np.abs(d_ex - 0.4) < MARGIN_TOL) | (np.abs(d_ex - 0.01) < MARGIN_TOL)
+            amb |= (np.abs(np.abs(o.positions) - 1.0) < MARGIN_TOL).any(axis=1) & (pre_st <= 2)
+            excluded.append(float(amb.mean()))
+            ok = ~amb
+            got_st = st["statuses"][e].cpu().numpy()
+            assert np.array_equal(got_st[ok], o.statuses[ok]), f"env {e}: statuses differ on an unambiguous pedestrian"
+            assert bool(trunc[e]) == bool(tr) and (bool(term[e]) == bool(tm) or amb.any())
+            _assert_close("positions", st["positions"][e].cpu().numpy()[ok], o.positions[ok])
+            alive = (o.statuses != 4)[:, None]
+            _assert_close("directions", (st["directions"][e].cpu().numpy() * alive)[ok], (o.directions * alive)[ok], scale=0.01, ill_conditioned=5e-2)
+            want = np.asarray(oobs, dtype=np.float64).reshape(n + 2, 6)
+            _assert_close("observation rows", flat[e][2:][ok], want[2:][ok], rtol=2e-5)
+            _assert_close("observation head", flat[e][:2], want[:2], rtol=2e-5)
+            if np.array_equal(got_st, o.statuses):  # the reward counts EVERY pedestrian's status transition
+                _assert_close("reward", reward[e].item(), r)
+    assert max(excluded) < 0.03, excluded
+    _record_summary("cluster_oracle", f"n{n}_cl{cluster}", dict(n=n, cluster=int(cluster), steps=steps, envs=E, excluded_fraction=excluded))
 
 
 def test_cell_list_nan_poisoning_matches_all_pairs():

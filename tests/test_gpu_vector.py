@@ -95,3 +95,42 @@ def test_vector_env_wrapper_chain_against_gymnasium_bookkeeping():
         else:
             assert "final_info" not in infos
     assert finished_total >= 3 * E   # truncation every 40 steps
+
+
+@pytest.mark.parametrize("wrap_kw,obs_dim", [(dict(), 4 + 2 * 20), (dict(positions="grav", alpha=3), 6), (dict(positions="rel", statuses="cat"), 4 + 3 * 20),
+                                             (dict(positions="rel", statuses="ohe", type="Box"), 22 * 6)])
+@pytest.mark.parametrize("E", [1, 4])
+def test_vector_env_every_wrapper_configuration_and_one_env(wrap_kw, obs_dim, E):
+    """Dict observations (the default EnvWrappersConfig, and positions='grav' as in run_scripts/learn_grav_emb.sh)
+    and the class default num_envs=1 go through the same flat row as the Box configuration: FlattenObservation order =
+    sorted Dict keys, checked against the structured observation of the raw batched env."""
+    import evacuation_b200 as eb
+
+    cfg = eb.EnvConfig(number_of_pedestrians=20, max_timesteps=7)
+    envs = eb.EvacuationVectorEnv(cfg, eb.EnvWrappersConfig(**wrap_kw), num_envs=E, seed=5, output="torch")
+    raw = eb.setup_env(cfg, eb.EnvWrappersConfig(**wrap_kw), num_envs=E, seed=5, auto_reset=True, batched=True)
+    assert envs.single_observation_space.shape == (obs_dim,)
+    o_v, _ = envs.reset()
+    o_r, _ = raw.reset()
+
+    def flat(o):
+        if isinstance(o, dict):
+            return torch.cat([o[k].reshape(E, -1) for k in sorted(o)], dim=1)
+        return o.reshape(E, -1)
+
+    assert o_v.shape == (E, obs_dim) and torch.equal(flat(o_r), raw.unwrapped.flat_observation)
+    for t in range(10):  # crosses a truncation + same-step auto-reset
+        act = torch.full((E, 2), 0.3, device="cuda")
+        o_v, r_v, term, trunc, infos = envs.step(act)
+        o_r, r_r, term_r, trunc_r, _ = raw.step(act)
+        assert o_v.shape == (E, obs_dim) and bool(torch.isfinite(o_v).all()) and float(o_v.abs().max()) <= 1.0
+        assert torch.equal(flat(o_r), raw.unwrapped.flat_observation)
+        assert torch.equal(term, term_r) and torch.equal(trunc, trunc_r)
+        if t == 6:
+            assert bool(trunc.all()) and infos["_final_info"].all()
+    envs.close()
+    with_numpy = eb.EvacuationVectorEnv(cfg, eb.EnvWrappersConfig(**wrap_kw), num_envs=E, seed=5)  # SyncVectorEnv-like host arrays
+    o, _ = with_numpy.reset()
+    o2, r, tm, tr, _ = with_numpy.step(np.zeros((E, 2), np.float32) + 0.3)
+    assert isinstance(o2, np.ndarray) and o2.shape == (E, obs_dim) and r.shape == (E,) and tm.dtype == bool
+    with_numpy.close()

@@ -127,6 +127,15 @@ def test_spaces_and_agents():
     box = Box(low=-1.0, high=1.0, shape=(2,), dtype=np.float32)
     a = eb.RandomAgent(box).act(None)
     assert a.dtype == np.float32 and a.shape == (2,) and box.contains(a)
+    # the space samples from its own generator: the global MT19937 stream (which rng="numpy" retraces the reference with)
+    # is left untouched, and seeding the space makes its samples reproducible (gymnasium semantics)
+    np.random.seed(123)
+    before = np.random.get_state()[1].copy(), np.random.get_state()[2]
+    box.sample(); eb.RandomAgent(box).act(None)
+    after = np.random.get_state()[1], np.random.get_state()[2]
+    assert np.array_equal(before[0], after[0]) and before[1] == after[1]
+    box.seed(7); s1 = box.sample(); box.seed(7)
+    assert np.array_equal(s1, box.sample())
     r = eb.RotatingAgent(box)
     assert np.allclose(r.act(None), [np.sin(0.05), np.cos(0.05)]) and np.allclose(r.act(None), [np.sin(0.1), np.cos(0.1)])
 
@@ -145,6 +154,46 @@ def test_philox_known_answers():
         assert (int(got[0]), int(got[1])) == want
     nz = T.philox_noise(7, 3, 1, 0, 60, 0.2)
     assert nz.dtype == np.float32 and np.all(np.abs(nz) <= 0.1) and len(np.unique(nz)) > 50
+
+
+def test_noise_streams_do_not_alias_for_large_crowds(tmp_path):
+    """with the block index OR-ed into the step field, pedestrian i + 4096 at step t drew pedestrian i's noise of
+    step t + 1 (crowds above 4096).  (a) no two (pedestrian pair, step) tuples of one episode share a noise block any more;
+    (b) the C++ stream (csrc/philox.cuh, compiled for the host) equals the NumPy restatement used by the parity tests."""
+    n = 32768
+    rows = np.stack([T.philox_noise(2024, 7, 3, now, n, 0.2) for now in (0, 1, 2, 7, 8, 15, 1999)])
+    for r in rows:  # rows i and i + 4096 k differ within a step ...
+        for k in range(1, 8):
+            assert not np.array_equal(r[: n - 4096 * k], r[4096 * k:])
+    flat = rows[:, ::1].reshape(len(rows), -1)
+    for a in range(len(rows)):  # ... and no step is a shifted copy of another one
+        for b_ in range(a + 1, len(rows)):
+            for k in range(0, 8):
+                assert not np.array_equal(flat[a][4096 * k: 4096 * k + 4096], flat[b_][:4096]), (a, b_, k)
+    assert len(np.unique(rows[0])) > 0.99 * 2 ** 15 * (1 - 2 ** -10)  # 24-bit uniforms: almost no repeats among 32768 draws
+    import shutil
+
+    from evacuation_b200 import build as b
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = tmp_path / "noise.cu"
+    src.write_text('#include <cstdio>\n#include <cuda_runtime.h>\n#include "philox.cuh"\nusing namespace evac;\n'
+                   "int main() { const unsigned nows[3] = {0u, 7u, 1999u};\n"
+                   "  for (unsigned t = 0; t < 3; ++t) for (unsigned i = 0; i < 32768u; i += 61u) {\n"
+                   "    const uint2 r = evac_noise_block(2024ull, 7u, 3u, nows[t], evac_noise_block_of(i));\n"
+                   '    printf("%u %u %.9g\\n", nows[t], i, (double)((u01(evac_noise_word_of(i) ? r.y : r.x) - 0.5f) * 0.2f)); }\n'
+                   "  return 0; }\n")
+    exe = tmp_path / "noise"
+    res = subprocess.run([nvcc, "-std=c++17", "-O1", "-I", b.CSRC, str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()
+    want = {0: T.philox_noise(2024, 7, 3, 0, n, 0.2), 7: T.philox_noise(2024, 7, 3, 7, n, 0.2), 1999: T.philox_noise(2024, 7, 3, 1999, n, 0.2)}
+    vals = np.array(out, dtype=np.float64).reshape(-1, 3)
+    assert len(vals) == 3 * len(range(0, 32768, 61))
+    for now, i, v in vals:
+        assert np.float32(v) == want[int(now)][int(i)], (now, i)
 
 
 def test_shard_partition():

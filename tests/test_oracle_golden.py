@@ -59,3 +59,28 @@ def test_kat0_values():
     assert z["pos_sum"][-1] == 8.936291463364315 and z["dir_sum"][-1] == 0.1050649092566393
     st = z["statuses"][-1]
     assert [(st == k).sum() for k in (4, 3, 2, 1)] == [6, 0, 5, 49]
+
+
+@pytest.mark.parametrize("n,chunk", [(60, 7), (600, 64), (700, 1), (1500, 333)])
+def test_row_chunked_alignment_is_bit_identical(n, chunk):
+    """The > 8192-pedestrian parity cases evaluate area.py:105-119 on blocks of rows of the |fv| x |efv| distance matrix
+    (32768^2 float64 entries do not fit in memory).  Every row's neighbour sums are reductions along the contiguous axis,
+    so the blocked evaluation must give the same BITS as the one-expression evaluation the goldens pin."""
+    from evac_testlib import OracleConfig
+
+    cfg = OracleConfig(number_of_pedestrians=n, is_new_exiting_reward=True, intrinsic_reward_coef=0.5, enslaving_degree=0.6, noise_coef=0.4)
+    envs = []
+    for rc in (None, chunk):
+        env = OracleEnv(cfg)
+        env.row_chunk = rc
+        np.random.seed(n)
+        env.reset()
+        env.positions[: n // 3] = np.array([0.4, 0.3]) + np.random.RandomState(1).normal(0, 0.03, (n // 3, 2))  # a dense blob
+        envs.append(env)
+    rs = np.random.RandomState(2)
+    for t in range(4):
+        a = rs.uniform(-1, 1, 2).astype(np.float32)
+        nz = rs.uniform(-0.2, 0.2, n)
+        outs = [e.step(a.copy(), nz.copy()) for e in envs]
+        assert outs[0][1] == outs[1][1] and outs[0][4].margin == outs[1][4].margin
+        assert _eq(envs[0].positions, envs[1].positions) and _eq(envs[0].directions, envs[1].directions) and _eq(envs[0].statuses, envs[1].statuses)

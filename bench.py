@@ -117,24 +117,70 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU side: the oracle port of the reference's per-env step loop (the reference itself is pure
-# Python and does not travel to the GPU box; oracle/evac_oracle.py is proven bit-identical to it).
-def _cpu_worker(args, n_ped=None):
-    n_envs, steps, warmup, seed, barrier = args
+# CPU side: the reference's own per-env step loop (src/env/__init__.py:18-21 -> src/env/env/env.py:141-171) on the host
+# cores.  kind = "reference": the UNMODIFIED reference, imported through oracle/ref_shim.py from $EVAC_REFERENCE_ROOT,
+# /root/reference or baseline/_ref (the pip --target install made by oracle/install_reference.py, which travels to the GPU
+# box); kind = "port": oracle/evac_oracle.py (bit-identical to the reference on tests/golden/) when no copy is reachable.
+def cpu_kind():
+    from oracle import ref_shim
+
+    if os.environ.get("EVAC_BENCH_CPU_KIND") == "port":  # A/B and tests: force the port although the reference is reachable
+        return "port"
+    return "reference" if ref_shim.reference_available() else "port"
+
+
+_REF_LOG_DIR = None
+
+
+def _make_cpu_env(kind, n_ped, env_kw=None, wrap_kw=None):
+    kw = dict(ENV_KW) if env_kw is None else dict(env_kw)
+    if n_ped is not None:
+        kw["number_of_pedestrians"] = n_ped
+    WRAP_KW_ = WRAP_KW if wrap_kw is None else wrap_kw
+    if kind == "reference":
+        import tempfile
+        import warnings
+
+        from oracle import ref_shim
+
+        warnings.filterwarnings("ignore")
+        ref = ref_shim.load_reference()
+        global _REF_LOG_DIR
+        if _REF_LOG_DIR is None:  # one scratch log directory per process (the reference opens a log file per env, env.py:23-31)
+            import atexit
+            import shutil
+
+            _REF_LOG_DIR = tempfile.mkdtemp(prefix="evac_ref_logs_")
+            atexit.register(shutil.rmtree, _REF_LOG_DIR, ignore_errors=True)
+        cfg = ref.EnvConfig(wandb_enabled=False, giff_freq=10 ** 9, path_logs=_REF_LOG_DIR, **kw)
+        return ref.setup_env(cfg, ref.EnvWrappersConfig(**WRAP_KW_))
     from oracle.evac_oracle import OracleConfig, OracleEnv
 
-    kw = dict(ENV_KW) if n_ped is None else dict(ENV_KW, number_of_pedestrians=n_ped)
-    cfg = OracleConfig(**kw, **WRAP_KW)
-    envs = []
+    class _Port:  # same call shape as the reference env
+        def __init__(self):
+            self.env = OracleEnv(OracleConfig(**kw, **WRAP_KW_))
+
+        def reset(self):
+            return self.env.reset(), {}
+
+        def step(self, a):
+            return self.env.step(a)
+
+    return _Port()
+
+
+def _cpu_worker(args, n_ped=None, kind="port"):
+    n_envs, steps, warmup, seed, barrier = args
     np.random.seed(seed)
+    envs = []
     for _ in range(n_envs):
-        e = OracleEnv(cfg)
+        e = _make_cpu_env(kind, n_ped)
         e.reset()
         envs.append(e)
     rs = np.random.RandomState(seed + 1)
 
     def one_step():
-        for e in envs:
+        for e in envs:  # the reference's user loop (README.md:79-86): RandomAgent action, step, reset when the episode ends
             _, _, term, trunc, _ = e.step(rs.uniform(-1, 1, 2).astype(np.float32))
             if term or trunc:
                 e.reset()
@@ -146,42 +192,114 @@ def _cpu_worker(args, n_ped=None):
     t0 = time.perf_counter()
     for _ in range(steps):
         one_step()
-    return time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    global _REF_LOG_DIR
+    if _REF_LOG_DIR is not None:  # (forked workers leave through os._exit: atexit handlers do not run there)
+        import logging
+        import shutil
+
+        logging.shutdown()
+        shutil.rmtree(_REF_LOG_DIR, ignore_errors=True)
+        _REF_LOG_DIR = None
+    return dt
 
 
 def cpu_baseline_single_core(target_seconds=12.0):
-    """Oracle port on ONE core: one env x 60 pedestrians (C1-like loop with the C2 wrappers), ~target_seconds."""
-    t = _cpu_worker((1, 200, 20, 0, None))
+    """The CPU step loop on ONE core: one env x 60 pedestrians (C1-like loop with the C2 wrappers), ~target_seconds;
+    the reference itself when reachable (and the port beside it), else the port."""
+    kind = cpu_kind()
+    t = _cpu_worker((1, 200, 20, 0, None), kind=kind)
     steps = max(200, int(200 * target_seconds / max(t, 1e-3)))
     steps = min(steps, 200000)
-    t = _cpu_worker((1, steps, 20, 0, None))
+    t = _cpu_worker((1, steps, 20, 0, None), kind=kind)
     env_sps = steps / t
     # SURVEY 8(d)(iii): the large-crowd config (C4) on one core, 1 env x 4096 pedestrians, a handful of steps (~1 step/s)
-    t4 = _cpu_worker((1, 5, 1, 0, None), n_ped=4096)
-    return {"value": env_sps * N_PED, "unit": "pedestrian-steps/s", "env_steps_per_s": env_sps, "cores": 1, "kind": "port",
-            "sample": f"oracle/evac_oracle.py (NumPy fp64 port, bit-identical to the reference on tests/golden), 1 env x {N_PED} pedestrians, "
-                      f"{steps} steps in {t:.1f} s on 1 core, rel+ohe Box observation",
-            "c4_1x4096": {"value": 5 * 4096 / t4, "unit": "pedestrian-steps/s", "env_steps_per_s": 5 / t4,
-                          "sample": f"1 env x 4096 pedestrians, 5 steps in {t4:.1f} s on 1 core"}}
+    t4 = _cpu_worker((1, 5, 1, 0, None), n_ped=4096, kind=kind)
+    what = ("the UNMODIFIED reference (src/env through oracle/ref_shim.py)" if kind == "reference" else
+            "oracle/evac_oracle.py (NumPy fp64 port, bit-identical to the reference on tests/golden; no copy of the reference reachable)")
+    out = {"value": env_sps * N_PED, "unit": "pedestrian-steps/s", "env_steps_per_s": env_sps, "cores": 1, "kind": kind,
+           "sample": f"{what}, 1 env x {N_PED} pedestrians, {steps} steps in {t:.1f} s on 1 core, rel+ohe Box observation, RandomAgent actions",
+           "c4_1x4096": {"value": 5 * 4096 / t4, "unit": "pedestrian-steps/s", "env_steps_per_s": 5 / t4,
+                         "sample": f"1 env x 4096 pedestrians, 5 steps in {t4:.1f} s on 1 core"}}
+    if kind == "reference":  # the port on the same core, same loop (it is the checker of the parity tests)
+        tp = _cpu_worker((1, 2000, 20, 0, None), kind="port")
+        out["port_same_core"] = {"value": 2000 / tp * N_PED, "unit": "pedestrian-steps/s", "env_steps_per_s": 2000 / tp}
+    return out
+
+
+def c1_leg(dev, seeds=8, steps=2000):
+    """BASELINE.md section 3 item 1 / BASELINE.json configs[0] (C1): `EnvConfig(number_of_pedestrians=60)`, one 2000-step episode
+    per seed 0..7 (`np.random.seed(s)`, RandomAgent-like actions from `RandomState(1000 + s)`), 1 process / 1 core, with the
+    default wrappers (abs / no / Dict), rel + ohe + Box and grav (alpha 3) -- the reference's own README loop
+    (README.md:69-90), timed (a) on the CPU implementation (reference when reachable, else the port) and (b) through THIS
+    repo's drop-in single-env API (`setup_env(EnvConfig(60), wrap)`: NumPy in / NumPy out, rng="numpy" = the global MT19937
+    stream consumed like the reference, one fused kernel launch + one D2H copy per step).  Median over the seeds."""
+    import evacuation_b200 as eb
+
+    kind = cpu_kind()
+    out = {"cpu_kind": kind, "cores": 1, "seeds": seeds, "steps_per_episode": steps, "cases": {}}
+    for name, wrap in (("abs_no_dict", {}), ("rel_ohe_box", WRAP_KW), ("grav_alpha3_dict", dict(positions="grav", alpha=3))):
+        rates = {"cpu": [], "gpu": []}
+        for arm in ("cpu", "gpu"):
+            for seed in range(seeds):
+                if arm == "cpu":
+                    env = _make_cpu_env(kind, None, env_kw=dict(number_of_pedestrians=N_PED), wrap_kw=wrap)
+                else:
+                    env = eb.setup_env(eb.EnvConfig(number_of_pedestrians=N_PED, wandb_enabled=False), eb.EnvWrappersConfig(**wrap), device=dev)
+                np.random.seed(seed)
+                rs = np.random.RandomState(1000 + seed)
+                acts = rs.uniform(-1, 1, size=(steps, 2)).astype(np.float32)
+                env.reset()
+                if arm == "gpu" and seed == 0:
+                    for t in range(20):  # module load / first-launch costs are not the step
+                        env.step(acts[t])
+                    np.random.seed(seed)
+                    env.reset()
+                done = 0
+                t0 = time.perf_counter()
+                for t in range(steps):
+                    _, _, term, trunc, _ = env.step(acts[t])
+                    done += 1
+                    if term or trunc:
+                        break
+                rates[arm].append(done / (time.perf_counter() - t0))
+                if arm == "gpu":
+                    env.unwrapped.close()
+        cpu, gpu = float(np.median(rates["cpu"])), float(np.median(rates["gpu"]))
+        out["cases"][name] = {"cpu_env_steps_per_s": cpu, "gpu_single_env_steps_per_s": gpu, "cpu_us_per_step": 1e6 / cpu,
+                              "gpu_single_env_us_per_step": 1e6 / gpu, "speedup_single_env": gpu / cpu}
+    global _REF_LOG_DIR
+    if _REF_LOG_DIR is not None:
+        import shutil
+
+        shutil.rmtree(_REF_LOG_DIR, ignore_errors=True)
+        _REF_LOG_DIR = None
+    return out
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference algorithm (oracle port) on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores, same workload (C2), same metric.
+    Every step advances a bounded sample of the 4096-env batch: all 4096 envs when K + W steps of them fit in about a
+    minute, else as many as do (the metric is rate-normalised).  At least ~10 s are timed regardless of --steps: the K-step
+    measurement is repeated back to back and the mean is reported."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    kind = cpu_kind()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # bounded sample: every step advances `envs_per_worker` envs per core; sized from a short calibration so that
-    # the whole --steps K --warmup W run takes about a minute of wall clock
-    t_cal = _cpu_worker((1, 60, 5, 99, None))
+    t_cal = _cpu_worker((1, 60, 5, 99, None), kind=kind)
     rate = 60.0 / max(t_cal, 1e-6)  # env-steps/s of one core
-    envs_per_worker = int(max(1, min(32, rate * 60.0 / max(args.steps + args.warmup, 1))))
+    steps_all = max(args.steps + args.warmup, 1)
+    envs_per_worker = int(max(1, min(-(-ENVS_PER_GPU // cores), rate * 60.0 / steps_all)))
+    est = envs_per_worker * args.steps / rate
+    min_seconds = float(os.environ.get("EVAC_BENCH_MIN_SECONDS", "10"))
+    passes = int(max(1, min(50, np.ceil(min_seconds / max(est, 1e-3)))))
     ctx = mp.get_context("fork")
     barrier = ctx.Barrier(cores)
     queue = ctx.Queue()
 
     def work(w):
-        queue.put(_cpu_worker((envs_per_worker, args.steps, args.warmup, 100 + w, barrier)))
+        queue.put(_cpu_worker((envs_per_worker, args.steps * passes, args.warmup, 100 + w, barrier), kind=kind))
 
     procs = [ctx.Process(target=work, args=(w,)) for w in range(cores)]
     for p in procs:
@@ -189,17 +307,19 @@ def run_reference_arm(args):
     times = [queue.get() for _ in procs]
     for p in procs:
         p.join()
-    t = max(times)
+    t = max(times) / passes  # mean duration of one K-step pass
     env_steps = cores * envs_per_worker * args.steps
     value = env_steps * N_PED / t
-    sample = (f"oracle port (kind=port; the reference is pure Python and is not installable/shipped: no setup.py), {cores} worker processes x "
-              f"{envs_per_worker} envs x {N_PED} pedestrians, {args.steps} steps each, max worker time {t:.2f} s")
+    what = ("UNMODIFIED reference (kind=reference: src/env imported through oracle/ref_shim.py)" if kind == "reference" else
+            "oracle port (kind=port: no copy of the reference reachable on this box)")
+    sample = (f"{what}, {cores} worker processes x {envs_per_worker} envs x {N_PED} pedestrians = {cores * envs_per_worker} of the "
+              f"{ENVS_PER_GPU} envs per step, {passes} back-to-back passes of {args.steps} steps, mean pass time {t:.2f} s (max over workers)")
     line = {
         "impl": "reference", "metric": "pedestrian-steps/s", "value": value, "unit": "pedestrian-steps/s", "env_steps_per_s": env_steps / t,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{cores * envs_per_worker} envs per step on the host CPUs"},
-        "cpu_baseline": {"value": value, "unit": "pedestrian-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": f"{cores * envs_per_worker} envs per step on the host CPUs", "passes": passes},
+        "cpu_baseline": {"value": value, "unit": "pedestrian-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pedestrian-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -271,17 +391,32 @@ def run_ours(args):
         sets.append(er)
     sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the same K steps are also bracketed by two event-record NODES inside the graph (external events): they time the K
+    # step kernels alone, without the launch latency of the graph itself -- which the device pays once per replay, not once
+    # per step (it is ~0.4 us per step at the driver's K = 20 and vanishes at K = 2000).  Both numbers are reported.
+    g0, g1 = torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)
     graph_a, side = torch.cuda.CUDAGraph(), torch.cuda.Stream(device=dev)
     torch.cuda.synchronize(dev)
     launches0 = sum(x.unwrapped.launch_count for x in sets)
+    ingraph_ok = True
     with torch.cuda.stream(side):
         with torch.cuda.graph(graph_a, stream=side):
+            try:
+                g0.record()
+            except Exception:  # pragma: no cover
+                ingraph_ok = False
             for s in range(K):
                 sets[s % R].unwrapped.step(actions[W + s])
+            if ingraph_ok:
+                g1.record()
     torch.cuda.synchronize(dev)
     # kernel nodes recorded into the graph (the library counts launches at capture time) = launches of ONE timed replay
     launches = sum(x.unwrapped.launch_count for x in sets) - launches0
-    graph_a.replay()  # untimed: graph upload + one more pass over every set
+    # untimed warm-up replays (beyond the W steps above): graph upload, and ~30 ms of the very workload so that the timed
+    # replay runs at settled clocks / warm instruction caches (the first replays of a freshly launched process are ~5 % slower)
+    ramp = int(min(500, max(2, np.ceil(0.03 / (K * 10e-6)))))
+    for _ in range(ramp):
+        graph_a.replay()
     barrier()
     sampler.start()
     # device head start: the GPU spins while the host submits the K-node graph launch, so that a host thread that is briefly
@@ -293,7 +428,16 @@ def run_ours(args):
     graph_a.replay()
     e1.record()
     barrier()
-    kernel_ms = e0.elapsed_time(e1)
+    outer_ms = e0.elapsed_time(e1)
+    kernel_ms = outer_ms
+    timed_by = "CUDA events around the graph replay"
+    if ingraph_ok:
+        try:
+            inner = g0.elapsed_time(g1)
+            if 0.0 < inner <= outer_ms:
+                kernel_ms, timed_by = inner, "CUDA event-record nodes inside the graph, around the K step kernels"
+        except Exception:  # pragma: no cover
+            pass
     del graph_a
     for er in sets[1:]:
         er.unwrapped.close()
@@ -365,12 +509,29 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- north-star config C5 (65 536 envs in total, policy in the loop) on THIS run's ranks, strong scaling
+    c5 = None
+    if not args.no_c5:
+        try:
+            c5 = c5_leg(args, dev, world, rank, barrier)
+        except Exception as exc:  # pragma: no cover
+            c5 = {"error": repr(exc)}
     per_rank_us = [1e3 * kernel_ms / K]
     if world > 1:
         t = torch.zeros(world, dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(t, torch.tensor([1e3 * kernel_ms / K], dtype=torch.float64, device=dev))
         per_rank_us = [float(x) for x in t.tolist()]
-    kernel_ms, flushed_ms, resident_ms, rollout_ms, e2e_s = maxr(kernel_ms), maxr(flushed_ms), maxr(resident_ms), maxr(rollout_ms), maxr(e2e_s)
+    kernel_ms, outer_ms, flushed_ms, resident_ms, rollout_ms, e2e_s = (maxr(kernel_ms), maxr(outer_ms), maxr(flushed_ms), maxr(resident_ms),
+                                                                        maxr(rollout_ms), maxr(e2e_s))
+    if c5 is not None and "ms" in c5:
+        c5_by_rank = [c5["ms"]]
+        if world > 1:
+            t = torch.zeros(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(t, torch.tensor([c5["ms"]], dtype=torch.float64, device=dev))
+            c5_by_rank = [float(x) for x in t.tolist()]
+        c5["ms"] = maxr(c5["ms"])
+        c5["finite"] = bool(maxr(0.0 if c5["finite"] else 1.0) == 0.0)
+        c5["ms_per_iteration_by_rank"] = [x / c5["steps"] for x in c5_by_rank]
     totals = allgather_episode_totals(u)  # the only collective: finished-episode statistics
 
     if rank == 0:
@@ -381,11 +542,12 @@ def run_ours(args):
         bytes_launch = algorithmic_bytes_per_env_step(N_PED, obs_dim * 4) * E
         flops_launch = algorithmic_flops_per_env_step(N_PED) * E
         launch_s = kernel_ms * 1e-3 / K
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath):  # dram__bytes of the dominant kernel, captured by ncu IN THE TIMED REGIME (rotating batches, no cache flush)
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal; measured FMA probe in profiles/
         line = {
             "metric": "pedestrian-steps/s", "value": value, "unit": "pedestrian-steps/s", "env_steps_per_s": env_steps / (kernel_ms * 1e-3),
@@ -394,11 +556,13 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "envs_per_gpu": E, "pedestrians": N_PED, "obs": "rel+ohe Box [62,6] f32",
                        "actions": "U[-1,1]^2 table resident in HBM", "noise": "in-kernel Philox2x32-10", "auto_reset": True,
                        "l2": f"inputs larger than L2: {R} independent C2 batches ({R} x {bytes_launch / 1e6:.1f} MB algorithmic traffic vs 126 MB L2) "
-                             "stepped round-robin, one batch per step, K launches in one CUDA graph, CUDA events around the replay",
+                             "stepped round-robin, one batch per step, K launches in one CUDA graph",
+                       "timed_by": timed_by, "ms_per_step_incl_graph_launch": outer_ms / K, "untimed_warmup_replays": ramp,
                        "sets": R, "pdl": bool(int(os.environ.get("EVAC_PDL", "0") or 0)),
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": bytes_launch / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": bytes_launch / launch_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": bytes_launch / launch_s / 1e9 / hbm_peak, "traffic": traffic, "traffic_over_algorithmic": (traffic / bytes_launch) if traffic else None,
+                         "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "evac_warp_kernel<WMODE_REL_OHE_BOX> (one warp per environment)", "algorithmic_bytes_per_launch": bytes_launch},
             "roofline_fp32": {"bound": "fp32", "achieved": flops_launch / launch_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                               "frac": flops_launch / launch_s / 1e12 / fp32_peak, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
@@ -416,9 +580,21 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "us_per_step_by_rank": per_rank_us,
+            "build_id": _build_id(),
             "episodes_finished_all_ranks": float(totals[:, 0].sum()),
         }
+        if c5 is not None and "ms" in c5:
+            ms5 = c5.pop("ms")
+            c5.update({"metric": "pedestrian-steps/s", "value": c5["total_envs"] * c5["steps"] * N_PED / (ms5 * 1e-3), "unit": "pedestrian-steps/s",
+                       "env_steps_per_s": c5["total_envs"] * c5["steps"] / (ms5 * 1e-3), "ms_per_iteration": ms5 / c5["steps"], "n_gpus": world,
+                       "scaling": "strong", "target": "north_star: >= 1e10 pedestrian-steps/s on 8 x B200"})
+        if c5 is not None:
+            line["c5"] = c5
         # the secondary legs must never cost the contract line: a failure is reported inside it
+        try:
+            line["roofline_pairwise"] = pairwise_probe(local_rank)
+        except Exception as exc:  # pragma: no cover
+            line["roofline_pairwise"] = {"error": repr(exc)}
         if world == 1 and not args.no_extra:
             try:
                 line["other_workloads"] = other_workloads(dev)
@@ -429,44 +605,169 @@ def run_ours(args):
                 line["cpu_baseline"] = cpu_baseline_single_core(args.cpu_seconds)
             except Exception as exc:  # pragma: no cover
                 line["cpu_baseline"] = {"error": repr(exc), "kind": "port", "cores": 1}
+            try:
+                line["c1_single_env"] = c1_leg(dev)
+            except Exception as exc:  # pragma: no cover
+                line["c1_single_env"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _build_id():
+    from evacuation_b200 import _native as nat
+
+    return nat.build_id()
+
+
+def pairwise_probe(device_index):
+    """north_star: ">= 50 % of the FP32 roofline on the pairwise alignment kernel".  Standalone launches of the SAME
+    `pairwise_pass` device function the fused step uses (probe_pairwise_kernel<32, 2>: one warp per environment, two
+    pedestrians per lane), N = 60, at the bench batch and at the C5 batch; 8 algorithmic flops per ordered pair (SURVEY 8d);
+    peak = the FFMA2 probe measured in the same process (nominal 148 x 128 x 2 x 1.965 GHz = 74.4 TFLOP/s beside it)."""
+    import ctypes as C
+
+    from evacuation_b200 import _native as nat
+
+    lib = nat.load()
+    ms, fl, pairs = C.c_float(), C.c_double(), C.c_double()
+    peak = 0.0
+    for _ in range(3):
+        nat.check(lib.evac_probe_fma(device_index, 1, 20000, C.byref(ms), C.byref(fl)))
+        peak = max(peak, fl.value / (ms.value * 1e-3) / 1e12)
+    out = {"bound": "fp32", "unit": "TFLOP/s", "peak": peak, "peak_source": "FFMA2 probe (evac_probe_fma) in this process",
+           "peak_nominal": 148 * 128 * 2 * 1.965e9 / 1e12, "kernel": "probe_pairwise_kernel<32,2>: pairwise_pass<2,false,4> of the fused step, standalone",
+           "flops_per_ordered_pair": 8, "cases": {}}
+    for E, reps in ((ENVS_PER_GPU, 200), (65536, 50)):
+        best = 0.0
+        for _ in range(3):
+            nat.check(lib.evac_probe_pairwise(device_index, E, N_PED, reps, C.byref(ms), C.byref(pairs)))
+            best = max(best, pairs.value / (ms.value * 1e-3))
+        out["cases"][f"{E}x{N_PED}"] = {"achieved": best * 8 / 1e12, "frac": best * 8 / 1e12 / peak, "frac_of_nominal": best * 8 / out["peak_nominal"] / 1e12,
+                                         "ordered_pairs_per_s": best}
+    head = out["cases"][f"{ENVS_PER_GPU}x{N_PED}"]
+    out["achieved"], out["frac"] = head["achieved"], head["frac"]
+    return out
+
+
+def c5_leg(args, dev, world, rank, barrier):
+    """BASELINE config 5 inside the contract run, for EVERY --gpus N: 65 536 envs x 60 pedestrians in TOTAL, sharded over the
+    ranks (strong scaling), the RPO transformer-embedding policy in the rollout loop (rpo_agent.py:180-203: fused CUDA
+    policy -> fused env step -> reward normaliser, 4 launches per iteration, CUDA-graph replayed, dropout active).  Returns
+    this rank's device time; the caller takes the max over ranks."""
+    import torch
+
+    import evacuation_b200 as eb
+    from evacuation_b200.distributed import shard_offset
+    from evacuation_b200.rollout import FusedRPOTransformerPolicy, PolicyRollout, RPOTransformerPolicy
+
+    total = 65536
+    E = total // world
+    K5, W5 = int(min(max(args.steps, 1), 64)), int(min(max(args.warmup, 3), 16))
+    env = eb.setup_env(eb.EnvConfig(**ENV_KW), eb.EnvWrappersConfig(**WRAP_KW), num_envs=E, device=dev, seed=args.seed, auto_reset=True,
+                       env_index_offset=shard_offset(rank, E))
+    torch.manual_seed(1)  # every rank holds the same policy replica
+    net = RPOTransformerPolicy(env.unwrapped.obs_dim, N_PED).to(dev)
+    pol = FusedRPOTransformerPolicy(net, N_PED, device=dev, seed=args.seed, env_index_offset=shard_offset(rank, E))
+    ro = PolicyRollout(env, pol, use_graph=True, store=False)
+    ro.reset()
+    ro.run(W5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    ro.run(K5)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    out = {"ms": ms, "steps": K5, "warmup": W5, "total_envs": total, "envs_per_gpu": E, "finite": bool(torch.isfinite(ro.out["value"]).all()),
+           "gpu_launches": int((ro.launches_per_iteration or 0) * K5), "launches_per_iteration": ro.launches_per_iteration,
+           "workload": "C5: 65536 envs x 60 pedestrians in total, env-sharded, RPO transformer-embedding policy (2 blocks, 3 heads, d_ff 96, dropout 0.1 "
+                       "active, MLP heads 372-64-64, random init seed 1) in the loop; one CUDA graph per iteration (4 kernels)",
+           "l2": "working set 4.5 KB per env: larger than L2 from 32768 envs per GPU; no flush"}
+    env.unwrapped.close()
+    del ro, pol, net
+    torch.cuda.empty_cache()
+    return out
+
+
 def other_workloads(dev):
     """Secondary BASELINE.json configs (parity-test cases, not the bench line): a short device-timed measurement of
-    each so that one bench run documents them.  K steps inside one rollout launch (on-device RandomAgent, same-step
-    auto-reset) after 64 warm-up steps; config 5 additionally with the RPO transformer-embedding policy in the loop."""
+    each so that one bench run documents them.  Two regimes per workload, labelled:
+      per_step : K calls of `env.step(actions)` (one launch each, observation written every step) captured in one CUDA graph;
+                 where one batch's working set is smaller than L2, R independent batches are stepped round-robin so that
+                 every step finds its state in HBM (same rule as the headline value);
+      rollout  : K steps inside ONE `evac_rollout` launch (state resident on chip, on-device RandomAgent, observation written
+                 after the last step only) -- the steady state of the kernel, NOT a per-step number.
+    HBM fractions use the algorithmic bytes of SURVEY 8(d) and are only quoted for the per_step regime (a rollout step moves
+    no state).  Config 5 additionally with the RPO transformer-embedding policy in the loop."""
     import torch
 
     import evacuation_b200 as eb
 
-    def rollout_us(env_kw, wrap_kw, E, K, **kw):
-        env = eb.setup_env(eb.EnvConfig(**env_kw), eb.EnvWrappersConfig(**wrap_kw), num_envs=E, device=dev, seed=7, auto_reset=True, **kw)
-        env.reset()
-        env.rollout(64, agent="random")
+    hbm_peak, _, _ = load_peaks()
+
+    def measure(env_kw, wrap_kw, E, K, R=1, **kw):
+        n = env_kw["number_of_pedestrians"]
+        sets = []
+        for r in range(R):
+            env = eb.setup_env(eb.EnvConfig(**env_kw), eb.EnvWrappersConfig(**wrap_kw), num_envs=E, device=dev, seed=7 + r, auto_reset=True, **kw)
+            env.reset()
+            env.rollout(64, agent="random")
+            sets.append(env)
+        g = torch.Generator(device=dev).manual_seed(99)
+        acts = torch.rand((K, E, 2), generator=g, device=dev) * 2 - 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream(device=dev)
         torch.cuda.synchronize(dev)
+        with torch.cuda.stream(side):
+            for env in sets:
+                env.unwrapped.step(acts[0])
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(graph, stream=side):
+                for s_ in range(K):
+                    sets[s_ % R].unwrapped.step(acts[s_])
+        torch.cuda.synchronize(dev)
+        graph.replay()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us_step = 1e3 * e0.elapsed_time(e1) / K
+        del graph
+        env = sets[0]
         e0.record()
         env.rollout(K, agent="random")
         e1.record()
         torch.cuda.synchronize(dev)
-        us = 1e3 * e0.elapsed_time(e1) / K
-        n = env_kw["number_of_pedestrians"]
-        env.unwrapped.close()
-        return {"envs": E, "pedestrians": n, "us_per_step": us, "pedestrian_steps_per_s": E * n / us * 1e6, "env_steps_per_s": E / us * 1e6,
-                "fp32_frac_algorithmic": E * algorithmic_flops_per_env_step(n) / (us * 1e-6) / (148 * 128 * 2 * 1.965e9)}
+        us_roll = 1e3 * e0.elapsed_time(e1) / K
+        obs_bytes = env.unwrapped.obs_dim * 4
+        bytes_step = algorithmic_bytes_per_env_step(n, obs_bytes) * E
+        for env in sets:
+            env.unwrapped.close()
+        return {"envs": E, "pedestrians": n, "batches_round_robin": R,
+                "per_step": {"us_per_step": us_step, "pedestrian_steps_per_s": E * n / us_step * 1e6, "env_steps_per_s": E / us_step * 1e6,
+                             "algorithmic_bytes_per_step": bytes_step, "hbm_GBps": bytes_step / us_step / 1e3,
+                             "hbm_frac": bytes_step / us_step / 1e3 / hbm_peak},
+                "rollout": {"us_per_step": us_roll, "pedestrian_steps_per_s": E * n / us_roll * 1e6, "env_steps_per_s": E / us_roll * 1e6,
+                            "note": "K steps in one launch; observation written after the last step only"}}
 
+    fp32_peak = 148 * 128 * 2 * 1.965e9
     out = {}
-    out["c3_grav_4096x60"] = rollout_us(dict(number_of_pedestrians=60, enslaving_degree=0.5, noise_coef=0.5), dict(positions="grav", alpha=3), 4096, 200)
-    out["c4_large_crowd_256x4096_cells"] = rollout_us(dict(number_of_pedestrians=4096), WRAP_KW, 256, 20)
-    out["c4_large_crowd_256x4096_all_pairs"] = rollout_us(dict(number_of_pedestrians=4096), WRAP_KW, 256, 4, neighbor_search="brute")
-    out["large_crowd_32x32768_cluster"] = rollout_us(dict(number_of_pedestrians=32768), WRAP_KW, 32, 8)  # one env per 8-CTA cluster
-    out["c5_env_only_65536x60"] = rollout_us(ENV_KW, WRAP_KW, 65536, 100)
+    out["c3_grav_4096x60"] = measure(dict(number_of_pedestrians=60, enslaving_degree=0.5, noise_coef=0.5), dict(positions="grav", alpha=3), 4096, 192, R=24)
+    out["c4_large_crowd_256x4096_cells"] = measure(dict(number_of_pedestrians=4096), WRAP_KW, 256, 20, R=4)
+    ap = measure(dict(number_of_pedestrians=4096), WRAP_KW, 256, 4, R=1, neighbor_search="brute")
+    for reg in ("per_step", "rollout"):  # all pairs: the only large-crowd leg whose work IS the algorithmic 8 N^2 flops
+        ap[reg]["fp32_frac_algorithmic"] = 256 * algorithmic_flops_per_env_step(4096) / (ap[reg]["us_per_step"] * 1e-6) / fp32_peak
+    out["c4_large_crowd_256x4096_all_pairs"] = ap
+    out["large_crowd_32x32768_cluster"] = measure(dict(number_of_pedestrians=32768), WRAP_KW, 32, 8, R=4)  # one env per thread-block cluster
+    c5 = measure(ENV_KW, WRAP_KW, 65536, 48, R=2)
+    for reg in ("per_step", "rollout"):
+        c5[reg]["fp32_frac_algorithmic"] = 65536 * algorithmic_flops_per_env_step(60) / (c5[reg]["us_per_step"] * 1e-6) / fp32_peak
+    out["c5_env_only_65536x60"] = c5
     # config 5, one rank's share of the 8-GPU job (65536 / 8 envs) with the policy in the loop: the fused CUDA policy
     # (evac_policy_forward: embedding kernel + heads kernel, NormalizeObservation / ClipAction fused) and, beside it, the
-    # same loop with the PyTorch restatement of the policy (library GEMMs / SDPA)
+    # same loop with the PyTorch restatement of the policy (library GEMMs / SDPA).  (65536 envs on this GPU: the `c5` object.)
     from evacuation_b200.rollout import FusedRPOTransformerPolicy, PolicyRollout, RPOTransformerPolicy
 
     def policy_loop_ms(E, fused, steps):
@@ -488,8 +789,7 @@ def other_workloads(dev):
         env.unwrapped.close()
         return ms
 
-    for E, fused, steps, key in ((8192, True, 64, "c5_policy_loop_8192x60"), (65536, True, 16, "c5_policy_loop_65536x60"),
-                                 (8192, False, 8, "c5_policy_loop_8192x60_torch_policy")):
+    for E, fused, steps, key in ((8192, True, 64, "c5_policy_loop_8192x60"), (8192, False, 8, "c5_policy_loop_8192x60_torch_policy")):
         ms = policy_loop_ms(E, fused, steps)
         out[key] = {"envs": E, "pedestrians": N_PED, "ms_per_step": ms, "pedestrian_steps_per_s": E * N_PED / ms * 1e3, "env_steps_per_s": E / ms * 1e3,
                     "note": ("fused CUDA policy (evac_policy_forward: NormalizeObservation + 2 transformer blocks, heads + Normal sampling + ClipAction) "
@@ -577,6 +877,7 @@ def main():
     ap.add_argument("--sets", type=int, default=24, help="independent batches stepped round-robin so that the inputs exceed L2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the other_workloads leg (secondary BASELINE configs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 leg (65536 envs in total with the policy in the loop)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = the bench line; c5 = config 5 with the policy in the loop")
     args = ap.parse_args()

@@ -11,7 +11,7 @@ import os
 from . import build as _build
 from .build import LIB_PATH
 
-EVAC_ABI_VERSION = 4
+EVAC_ABI_VERSION = 5
 NUM_EPISODE_STATS = 9
 EPISODE_STAT_KEYS = (  # env.py:115-125
     "episode_intrinsic_reward", "episode_status_reward", "episode_reward", "episode_length",
@@ -84,7 +84,7 @@ SIGNATURES = {
     "evac_get_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "evac_observe": (C.c_int, [_P, _P, _P]),
     "evac_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
-    "evac_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "evac_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "evac_rollout": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "evac_episode_stats": (C.c_int, [_P, _P, _P, _P, _P]),
     "evac_get_accumulators": (C.c_int, [_P, _P, _P, _P]),

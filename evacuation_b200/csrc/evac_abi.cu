@@ -58,14 +58,15 @@ struct EvacHandle {
   uint8_t* ep_finished = nullptr;
   double* totals = nullptr;
   int* agent_state = nullptr;
+  unsigned char* blocks = nullptr;  // EnvBlock layout (N <= 64 float32, one-warp kernel): replaces every array above
   // staging for the *_host entry points
   cudaStream_t stream = nullptr;
   float *h_actions = nullptr, *h_noise = nullptr, *h_obs = nullptr, *h_reward = nullptr;
-  const void* pin_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // evac_step_host: caller pointers of the last call ...
-  bool pin_val[6] = {false, false, false, false, false, false};                      // ... and whether each was page-locked
+  const void* pin_key[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // evac_step_host: caller pointers of the last call ...
+  bool pin_val[7] = {false, false, false, false, false, false, false};                        // ... and whether each was page-locked
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   float *d_actions = nullptr, *d_noise = nullptr, *d_obs = nullptr, *d_reward = nullptr;
-  uint8_t *d_term = nullptr, *d_trunc = nullptr;
+  uint8_t *d_term = nullptr, *d_trunc = nullptr, *d_status = nullptr, *h_status = nullptr;
   int64_t launches = 0;
   int threads = 0, ppt = 0;
   int num_sms = 0;
@@ -131,6 +132,7 @@ static KArgs<real> make_args(const EvacHandle* h) {
   a.now = h->now; a.episode = h->episode; a.overall = h->overall; a.acc = h->acc;
   a.ep_stats = h->ep_stats; a.ep_finished = h->ep_finished; a.totals = h->totals;
   a.agent_state = h->agent_state;
+  a.blocks = h->blocks;
   {  // baseline_wacuum_cleaner.py:17-28 (float64 expressions, compared against float32 positions -> rounded to float32)
     const double half_reach = c.to_leader / 2.0;
     a.wac_top = (float)(c.height - half_reach + c.step_size); a.wac_right = (float)(c.width - half_reach + c.step_size);
@@ -381,13 +383,18 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
     if (_e != cudaSuccess) { evac_destroy(h); return fail(EVAC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(_e)); } \
     cudaMemset((ptr), 0, (bytes));                                             \
   } while (0)
-  ALLOC(h->pos, en * es); ALLOC(h->dir, en * es); ALLOC(h->status, en);
-  ALLOC(h->agent_pos, (size_t)h->E * sizeof(float2)); ALLOC(h->agent_dir, (size_t)h->E * sizeof(float2));
-  ALLOC(h->now, (size_t)h->E * sizeof(int)); ALLOC(h->episode, (size_t)h->E * sizeof(int));
-  ALLOC(h->overall, (size_t)h->E * sizeof(long long)); ALLOC(h->acc, (size_t)h->E * 3 * sizeof(double));
+  if (h->threads == 32 && h->warp_kernel && h->prec == EVAC_PREC_F32) {
+    // the one-warp kernel family keeps the whole state of an environment in one packed 1152-byte block (EnvBlock)
+    ALLOC(h->blocks, (size_t)h->E * BLK_BYTES);
+  } else {
+    ALLOC(h->pos, en * es); ALLOC(h->dir, en * es); ALLOC(h->status, en);
+    ALLOC(h->agent_pos, (size_t)h->E * sizeof(float2)); ALLOC(h->agent_dir, (size_t)h->E * sizeof(float2));
+    ALLOC(h->now, (size_t)h->E * sizeof(int)); ALLOC(h->episode, (size_t)h->E * sizeof(int));
+    ALLOC(h->overall, (size_t)h->E * sizeof(long long)); ALLOC(h->acc, (size_t)h->E * 3 * sizeof(double));
+    ALLOC(h->agent_state, (size_t)h->E * sizeof(int));
+  }
   ALLOC(h->ep_stats, (size_t)h->E * EVAC_NUM_EPISODE_STATS * sizeof(float)); ALLOC(h->ep_finished, (size_t)h->E);
   ALLOC(h->totals, (1 + EVAC_NUM_EPISODE_STATS) * sizeof(double));
-  ALLOC(h->agent_state, (size_t)h->E * sizeof(int));
 #undef ALLOC
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaDeviceSynchronize());
@@ -400,7 +407,7 @@ int evac_destroy(EvacHandle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   void* dptrs[] = {h->pos, h->dir, h->status, h->agent_pos, h->agent_dir, h->now, h->episode, h->overall, h->acc,
-                   h->ep_stats, h->ep_finished, h->totals, h->agent_state, h->d_actions, h->d_noise, h->d_obs /* one block: obs | reward | flags */};
+                   h->ep_stats, h->ep_finished, h->totals, h->agent_state, h->blocks, h->d_actions, h->d_noise, h->d_obs /* one block: obs | reward | flags */};
   for (void* p : dptrs) if (p) cudaFree(p);
   void* hptrs[] = {h->h_actions, h->h_noise, h->h_obs /* one block */};
   for (void* p : hptrs) if (p) cudaFreeHost(p);
@@ -436,6 +443,14 @@ int evac_set_state(EvacHandle* h, const void* positions, const void* directions,
   if (int r = set_device(h)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t en = (size_t)h->E * h->N, es = h->prec == EVAC_PREC_F64 ? 16 : 8;
+  if (h->blocks) {
+    StateIO io = {(float2*)positions, (float2*)directions, (uint8_t*)statuses, (float2*)agent_position, (float2*)agent_direction, (int*)now, nullptr, nullptr};
+    evac_block_io_kernel<true><<<h->E, 64, 0, st>>>(h->blocks, h->E, h->N, io);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (!statuses && (positions || agent_position)) return launch_aux<float>(h, AUX_STATUS, nullptr, nullptr, st);
+    return EVAC_OK;
+  }
   if (positions) CK(cudaMemcpyAsync(h->pos, positions, en * es, cudaMemcpyDeviceToDevice, st));
   if (directions) CK(cudaMemcpyAsync(h->dir, directions, en * es, cudaMemcpyDeviceToDevice, st));
   if (agent_position) CK(cudaMemcpyAsync(h->agent_pos, agent_position, (size_t)h->E * 8, cudaMemcpyDeviceToDevice, st));
@@ -456,6 +471,13 @@ int evac_get_state(EvacHandle* h, void* positions, void* directions, uint8_t* st
   if (int r = set_device(h)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t en = (size_t)h->E * h->N, es = h->prec == EVAC_PREC_F64 ? 16 : 8;
+  if (h->blocks) {
+    StateIO io = {(float2*)positions, (float2*)directions, statuses, (float2*)agent_position, (float2*)agent_direction, now, nullptr, nullptr};
+    evac_block_io_kernel<false><<<h->E, 64, 0, st>>>(h->blocks, h->E, h->N, io);
+    CK(cudaGetLastError());
+    h->launches++;
+    return EVAC_OK;
+  }
   if (positions) CK(cudaMemcpyAsync(positions, h->pos, en * es, cudaMemcpyDeviceToDevice, st));
   if (directions) CK(cudaMemcpyAsync(directions, h->dir, en * es, cudaMemcpyDeviceToDevice, st));
   if (statuses) CK(cudaMemcpyAsync(statuses, h->status, en, cudaMemcpyDeviceToDevice, st));
@@ -465,9 +487,9 @@ int evac_get_state(EvacHandle* h, void* positions, void* directions, uint8_t* st
   return EVAC_OK;
 }
 
-int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const float* actions, const float* noise, float* obs,
-                 int32_t obs_every_step, float* reward_sum, uint8_t* terminated, uint8_t* truncated, uint16_t* status_counts,
-                 void* stream) {
+static int rollout_impl(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const float* actions, const float* noise, float* obs,
+                        int32_t obs_every_step, float* reward_sum, uint8_t* terminated, uint8_t* truncated, uint16_t* status_counts,
+                        uint8_t* status_out, void* stream) {
   if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
   if (num_steps < 1) return fail(EVAC_ERR_INVALID, "num_steps must be >= 1");
   if (agent_kind < EVAC_AGENT_TABLE || agent_kind > EVAC_AGENT_WACUUM) return fail(EVAC_ERR_INVALID, "invalid agent_kind");
@@ -478,14 +500,20 @@ int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const flo
     KArgs<double> a = make_args<double>(h);
     a.actions = (const float2*)actions; a.noise = noise; a.obs = obs; a.obs_every_step = obs_every_step;
     a.reward = reward_sum; a.terminated = terminated; a.truncated = truncated; a.num_steps = num_steps; a.agent_kind = agent_kind;
-    a.status_counts = status_counts;
+    a.status_counts = status_counts; a.status_out = status_out;
     return launch_step<double>(h, a, st);
   }
   KArgs<float> a = make_args<float>(h);
   a.actions = (const float2*)actions; a.noise = noise; a.obs = obs; a.obs_every_step = obs_every_step;
   a.reward = reward_sum; a.terminated = terminated; a.truncated = truncated; a.num_steps = num_steps; a.agent_kind = agent_kind;
-  a.status_counts = status_counts;
+  a.status_counts = status_counts; a.status_out = status_out;
   return launch_step<float>(h, a, st);
+}
+
+int evac_rollout(EvacHandle* h, int32_t num_steps, int32_t agent_kind, const float* actions, const float* noise, float* obs,
+                 int32_t obs_every_step, float* reward_sum, uint8_t* terminated, uint8_t* truncated, uint16_t* status_counts,
+                 void* stream) {
+  return rollout_impl(h, num_steps, agent_kind, actions, noise, obs, obs_every_step, reward_sum, terminated, truncated, status_counts, nullptr, stream);
 }
 
 int evac_step(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward, uint8_t* terminated,
@@ -502,51 +530,57 @@ static bool is_pinned(const void* p) {
 }
 
 int evac_step_host(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward, uint8_t* terminated,
-                   uint8_t* truncated) {
+                   uint8_t* truncated, uint8_t* statuses) {
   if (!h || !actions) return fail(EVAC_ERR_INVALID, "NULL argument");
   if (int r = set_device(h)) return r;
   const size_t E = h->E, N = h->N, D = h->obs_dim;
   if (!h->h_actions) {
     CK(cudaMallocHost((void**)&h->h_actions, E * 8)); CK(cudaMalloc((void**)&h->d_actions, E * 8));
-    // outputs live in ONE device block and ONE pinned block, [obs | reward | terminated | truncated], so a caller
+    // outputs live in ONE device block and ONE pinned block, [obs | reward | terminated | truncated | statuses], so a caller
     // whose (page-locked) result arrays are laid out the same way gets them with a single D2H copy
-    const size_t out_bytes = E * D * 4 + E * 4 + 2 * E;
+    const size_t out_bytes = E * D * 4 + E * 4 + 2 * E + E * N;
     unsigned char *hb = nullptr, *db = nullptr;
     CK(cudaMallocHost((void**)&hb, out_bytes)); CK(cudaMalloc((void**)&db, out_bytes));
-    h->h_obs = (float*)hb; h->h_reward = (float*)(hb + E * D * 4); h->h_term = hb + E * D * 4 + E * 4; h->h_trunc = h->h_term + E;
-    h->d_obs = (float*)db; h->d_reward = (float*)(db + E * D * 4); h->d_term = db + E * D * 4 + E * 4; h->d_trunc = h->d_term + E;
+    h->h_obs = (float*)hb; h->h_reward = (float*)(hb + E * D * 4); h->h_term = hb + E * D * 4 + E * 4; h->h_trunc = h->h_term + E; h->h_status = h->h_trunc + E;
+    h->d_obs = (float*)db; h->d_reward = (float*)(db + E * D * 4); h->d_term = db + E * D * 4 + E * 4; h->d_trunc = h->d_term + E; h->d_status = h->d_trunc + E;
   }
   if (noise && !h->h_noise) { CK(cudaMallocHost((void**)&h->h_noise, E * N * 4)); CK(cudaMalloc((void**)&h->d_noise, E * N * 4)); }
   cudaStream_t st = h->stream;
   // Page-locked caller buffers are used directly (zero staging copies); pageable ones go through the
   // handle's pinned staging buffers.
-  // (a caller that re-uses its buffers -- the Python host face does -- pays the six attribute queries once)
-  const void* ptrs[6] = {actions, noise, obs, reward, terminated, truncated};
-  for (int i = 0; i < 6; ++i)
+  // (a caller that re-uses its buffers -- the Python host face does -- pays the attribute queries once)
+  const void* ptrs[7] = {actions, noise, obs, reward, terminated, truncated, statuses};
+  for (int i = 0; i < 7; ++i)
     if (ptrs[i] != h->pin_key[i]) { h->pin_key[i] = ptrs[i]; h->pin_val[i] = is_pinned(ptrs[i]); }
-  const bool pa = h->pin_val[0], pn = h->pin_val[1], po = h->pin_val[2], pr = h->pin_val[3], pt = h->pin_val[4], pu = h->pin_val[5];
+  const bool pa = h->pin_val[0], pn = h->pin_val[1], po = h->pin_val[2], pr = h->pin_val[3], pt = h->pin_val[4], pu = h->pin_val[5], ps = h->pin_val[6];
   if (!pa) memcpy(h->h_actions, actions, E * 8);
   CK(cudaMemcpyAsync(h->d_actions, pa ? actions : h->h_actions, E * 8, cudaMemcpyHostToDevice, st));
   if (noise) {
     if (!pn) memcpy(h->h_noise, noise, E * N * 4);
     CK(cudaMemcpyAsync(h->d_noise, pn ? noise : h->h_noise, E * N * 4, cudaMemcpyHostToDevice, st));
   }
-  if (int r = evac_step(h, h->d_actions, noise ? h->d_noise : nullptr, obs ? h->d_obs : nullptr, h->d_reward, h->d_term, h->d_trunc, st)) return r;
-  const bool packed_pinned = po && pr && pt && pu && reward == obs + E * D && terminated == (uint8_t*)(reward + E) && truncated == terminated + E;
-  const bool all_pageable = !po && !pr && !pt && !pu && obs && reward && terminated && truncated;
+  if (int r = rollout_impl(h, 1, EVAC_AGENT_TABLE, h->d_actions, noise ? h->d_noise : nullptr, obs ? h->d_obs : nullptr, 0, h->d_reward, h->d_term,
+                           h->d_trunc, nullptr, statuses ? h->d_status : nullptr, st)) return r;
+  const size_t head_bytes = E * D * 4 + E * 4 + 2 * E;
+  const bool packed = reward == obs + E * D && terminated == (uint8_t*)(reward + E) && truncated == terminated + E &&
+                      (!statuses || statuses == truncated + E);
+  const bool packed_pinned = po && pr && pt && pu && (!statuses || ps) && obs && packed;
+  const bool all_pageable = !po && !pr && !pt && !pu && !ps && obs && reward && terminated && truncated;
   if (packed_pinned || all_pageable) {
-    CK(cudaMemcpyAsync(packed_pinned ? (void*)obs : (void*)h->h_obs, h->d_obs, E * D * 4 + E * 4 + 2 * E, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(packed_pinned ? (void*)obs : (void*)h->h_obs, h->d_obs, head_bytes + (statuses ? E * N : 0), cudaMemcpyDeviceToHost, st));
   } else {
     if (obs) CK(cudaMemcpyAsync(po ? obs : h->h_obs, h->d_obs, E * D * 4, cudaMemcpyDeviceToHost, st));
     if (reward) CK(cudaMemcpyAsync(pr ? reward : h->h_reward, h->d_reward, E * 4, cudaMemcpyDeviceToHost, st));
     if (terminated) CK(cudaMemcpyAsync(pt ? terminated : h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, st));
     if (truncated) CK(cudaMemcpyAsync(pu ? truncated : h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, st));
+    if (statuses) CK(cudaMemcpyAsync(ps ? statuses : h->h_status, h->d_status, E * N, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
   if (obs && !po) memcpy(obs, h->h_obs, E * D * 4);
   if (reward && !pr) memcpy(reward, h->h_reward, E * 4);
   if (terminated && !pt) memcpy(terminated, h->h_term, E);
   if (truncated && !pu) memcpy(truncated, h->h_trunc, E);
+  if (statuses && !ps) memcpy(statuses, h->h_status, E * N);
   return EVAC_OK;
 }
 
@@ -554,6 +588,13 @@ int evac_get_accumulators(EvacHandle* h, double* acc, int64_t* overall_timesteps
   if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
   if (int r = set_device(h)) return r;
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->blocks) {
+    StateIO io = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, acc, (long long*)overall_timesteps};
+    evac_block_io_kernel<false><<<h->E, 64, 0, st>>>(h->blocks, h->E, h->N, io);
+    CK(cudaGetLastError());
+    h->launches++;
+    return EVAC_OK;
+  }
   if (acc) CK(cudaMemcpyAsync(acc, h->acc, (size_t)h->E * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if (overall_timesteps) CK(cudaMemcpyAsync(overall_timesteps, h->overall, (size_t)h->E * sizeof(long long), cudaMemcpyDeviceToDevice, st));
   return EVAC_OK;

@@ -84,6 +84,9 @@ struct KArgs {
   uint8_t* ep_finished;            // [E]
   double* totals;                  // [1+9]
   int* agent_state;                // [E]   WacuumCleaner state machine (phase | heading << 2 | steps-down << 8)
+  // N <= 64 float32 handles (the one-warp kernel family) keep ALL of the above in one packed block per environment instead
+  // (EnvBlock below; the pointers above are NULL then)
+  unsigned char* blocks;           // [E, BLK_BYTES] or NULL
   // WacuumCleaner lane edges [baseline_wacuum_cleaner.py:17-28], compared in float32 like NumPy's weak-scalar promotion
   float wac_top, wac_right, wac_left, wac_bottom;
   // ---- per-call I/O
@@ -95,10 +98,95 @@ struct KArgs {
   uint8_t* terminated;    // [E]  (OR over steps)
   uint8_t* truncated;     // [E]
   uint16_t* status_counts;  // [steps,E,4] or NULL: escaped, exiting, following, viscek after every step (pedestrians.py:37-44)
+  uint8_t* status_out;      // [E,N] or NULL: dense copy of the statuses after the launch (host face: part of the result block)
   int num_steps, agent_kind;
   uint64_t seed;
   long long env_offset;
 };
+
+// ------------------------------------------------------------------------------------------
+// EnvBlock: packed per-environment state of the one-warp kernel family (N <= 64, float32).  Everything a step reads and
+// writes sits in ONE 1152-byte, 128-byte-aligned block, so the kernel forms one address per environment and every access
+// is that address + an immediate (+ 16 * lane): two broadcast LDG.128 for the record, one LDG.128 per pedestrian
+// ({px, py, dx, dy} interleaved), one LDG.U16 for the lane's two statuses -- and the mirror image for the write-back.
+//   [   0,   64)  EnvRec
+//   [  64,  128)  statuses: byte 2 l = pedestrian l, byte 2 l + 1 = pedestrian l + 32   (0 = padding slot)
+//   [ 128, 1152)  float4 {px, py, dx, dy} of pedestrian i at 128 + 16 i, 64 slots (slots >= N stay zero)
+struct __align__(16) EnvRec {
+  float2 agent_pos, agent_dir;     //  0: float32 like the reference's agent
+  int now, episode, agent_state, pad;  // 16: step in episode, episode index (Philox key word), WacuumCleaner state machine
+  long long overall;               // 32: overall_timesteps
+  double acc[3];                   // 40: episode_reward, episode_intrinsic_reward, episode_status_reward (env.py:168-170)
+};
+static_assert(sizeof(EnvRec) == 64, "EnvRec is one 64-byte record");
+constexpr int BLK_STATUS = 64, BLK_PED = 128, BLK_SLOTS = 64, BLK_BYTES = BLK_PED + 16 * BLK_SLOTS;
+__host__ __device__ __forceinline__ int blk_status_off(int i) { return BLK_STATUS + 2 * (i & 31) + (i >> 5); }
+
+// Layout-independent state access for the kernels OFF the per-step path (reset / status / observe / get / set state).
+template <typename real>
+__device__ __forceinline__ void state_load_ped(const KArgs<real>& a, int e, int i, real& px, real& py, real& dx, real& dy, int& st) {
+  if constexpr (std::is_same<real, float>::value) {
+    if (a.blocks != nullptr) {
+      const unsigned char* b = a.blocks + (size_t)e * BLK_BYTES;
+      const float4 v = reinterpret_cast<const float4*>(b + BLK_PED)[i];
+      px = v.x; py = v.y; dx = v.z; dy = v.w;
+      st = b[blk_status_off(i)];
+      return;
+    }
+  }
+  const typename vec2<real>::type p = a.pos[(size_t)e * a.N + i], d = a.dir[(size_t)e * a.N + i];
+  px = p.x; py = p.y; dx = d.x; dy = d.y;
+  st = a.status[(size_t)e * a.N + i];
+}
+template <typename real>
+__device__ __forceinline__ void state_store_ped(const KArgs<real>& a, int e, int i, real px, real py, real dx, real dy) {
+  if constexpr (std::is_same<real, float>::value) {
+    if (a.blocks != nullptr) {
+      reinterpret_cast<float4*>(a.blocks + (size_t)e * BLK_BYTES + BLK_PED)[i] = make_float4(px, py, dx, dy);
+      return;
+    }
+  }
+  typename vec2<real>::type p, d;
+  p.x = px; p.y = py; d.x = dx; d.y = dy;
+  a.pos[(size_t)e * a.N + i] = p;
+  a.dir[(size_t)e * a.N + i] = d;
+}
+template <typename real>
+__device__ __forceinline__ void state_store_status(const KArgs<real>& a, int e, int i, int st) {
+  if constexpr (std::is_same<real, float>::value) {
+    if (a.blocks != nullptr) { a.blocks[(size_t)e * BLK_BYTES + blk_status_off(i)] = (uint8_t)st; return; }
+  }
+  a.status[(size_t)e * a.N + i] = (uint8_t)st;
+}
+template <typename real>
+__device__ __forceinline__ EnvRec* state_rec(const KArgs<real>& a, int e) {
+  if constexpr (std::is_same<real, float>::value) return a.blocks ? reinterpret_cast<EnvRec*>(a.blocks + (size_t)e * BLK_BYTES) : nullptr;
+  else return nullptr;
+}
+template <typename real>
+__device__ __forceinline__ float2 state_agent_pos(const KArgs<real>& a, int e) {
+  const EnvRec* r = state_rec(a, e);
+  return r ? r->agent_pos : a.agent_pos[e];
+}
+template <typename real>
+__device__ __forceinline__ int state_episode(const KArgs<real>& a, int e) {
+  const EnvRec* r = state_rec(a, e);
+  return r ? r->episode : a.episode[e];
+}
+// thread 0 of a reset: agent at the origin, time and accumulators zeroed, next episode index (area.py:27-30,49-51; env.py:129-135)
+template <typename real>
+__device__ __forceinline__ void state_reset_rec(const KArgs<real>& a, int e, int episode) {
+  if (EnvRec* r = state_rec(a, e)) {
+    r->agent_pos = make_float2(0.f, 0.f); r->agent_dir = make_float2(0.f, 0.f);
+    r->now = 0; r->episode = episode; r->agent_state = 0;
+    r->acc[0] = r->acc[1] = r->acc[2] = 0.0;
+    return;
+  }
+  a.agent_state[e] = 0;
+  a.agent_pos[e] = make_float2(0.f, 0.f); a.agent_dir[e] = make_float2(0.f, 0.f);
+  a.now[e] = 0; a.episode[e] = episode;
+  a.acc[3 * (size_t)e] = a.acc[3 * (size_t)e + 1] = a.acc[3 * (size_t)e + 2] = 0.0;
+}
 
 // ------------------------------------------------------------------------------------------
 // small math helpers, float / double overloads
@@ -1068,6 +1156,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
         pos_e[i] = p;
         dir_e[i] = d;
         st_e[i] = (uint8_t)st[k];
+        if (a.status_out != nullptr) a.status_out[(size_t)e * N + i] = (uint8_t)st[k];
       }
     }
     if (lead) {
@@ -1093,7 +1182,6 @@ enum { AUX_RESET = 1, AUX_STATUS = 2, AUX_OBS = 4 };
 template <typename real>
 __global__ void __launch_bounds__(128) evac_aux_kernel(const __grid_constant__ KArgs<real> a, int flags,
                                                        const uint8_t* __restrict__ mask, float* __restrict__ obs) {
-  using real2 = typename vec2<real>::type;
   __shared__ RedScratch<4> red;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
@@ -1102,44 +1190,38 @@ __global__ void __launch_bounds__(128) evac_aux_kernel(const __grid_constant__ K
     const uint32_t env_g = (uint32_t)(a.env_offset + e);
     if ((flags & AUX_RESET) && sel) {
       __syncthreads();
-      const int episode = a.episode[e] + 1;
+      const int episode = state_episode(a, e) + 1;
       __syncthreads();
       for (int i = tid; i < N; i += 128) {
         real px, py, dx, dy, d2e;
         random_layout<real>(a.seed, env_g, (uint32_t)episode, (uint32_t)i, px, py, dx, dy);
-        real2 p, d;
-        p.x = px; p.y = py; d.x = dx; d.y = dy;
-        a.pos[(size_t)e * N + i] = p;
-        a.dir[(size_t)e * N + i] = d;
-        a.status[(size_t)e * N + i] = (uint8_t)status_of<real>(px, py, (real)0, (real)0, a, d2e);
+        state_store_ped<real>(a, e, i, px, py, dx, dy);
+        state_store_status<real>(a, e, i, status_of<real>(px, py, (real)0, (real)0, a, d2e));
       }
-      if (tid == 0) {
-        a.agent_state[e] = 0;
-        a.agent_pos[e] = make_float2(0.f, 0.f); a.agent_dir[e] = make_float2(0.f, 0.f);
-        a.now[e] = 0; a.episode[e] = episode;
-        a.acc[3 * (size_t)e] = a.acc[3 * (size_t)e + 1] = a.acc[3 * (size_t)e + 2] = 0.0;
-      }
+      if (tid == 0) state_reset_rec<real>(a, e, episode);
     }
     if ((flags & AUX_STATUS) && sel) {
-      const float2 ap = a.agent_pos[e];
+      const float2 ap = state_agent_pos(a, e);
       for (int i = tid; i < N; i += 128) {
-        const real2 p = a.pos[(size_t)e * N + i];
-        real d2e;
-        a.status[(size_t)e * N + i] = (uint8_t)status_of<real>(p.x, p.y, (real)ap.x, (real)ap.y, a, d2e);
+        real px, py, dx, dy, d2e;
+        int st;
+        state_load_ped<real>(a, e, i, px, py, dx, dy, st);
+        state_store_status<real>(a, e, i, status_of<real>(px, py, (real)ap.x, (real)ap.y, a, d2e));
       }
     }
     if ((flags & AUX_OBS) && obs != nullptr) {
       __syncthreads();  // this CTA's own global writes above are visible to it after the barrier
-      float2 ap = a.agent_pos[e];
+      float2 ap = state_agent_pos(a, e);
       if ((flags & AUX_RESET) && sel) ap = make_float2(0.f, 0.f);
       float* row = obs + (size_t)e * a.obs_dim;
       if (a.positions == POS_GRAV) {
         real gx = (real)0, gy = (real)0;
         int nf = 0;
         for (int i = tid; i < N; i += 128) {
-          const real2 p = a.pos[(size_t)e * N + i];
-          const int s = a.status[(size_t)e * N + i];
-          if (s == ST_VISCEK) { real tx, ty; grav_term<real>(p.x, p.y, ap.x, ap.y, a, tx, ty); gx += tx; gy += ty; }
+          real px, py, dx, dy;
+          int s;
+          state_load_ped<real>(a, e, i, px, py, dx, dy, s);
+          if (s == ST_VISCEK) { real tx, ty; grav_term<real>(px, py, ap.x, ap.y, a, tx, ty); gx += tx; gy += ty; }
           nf += (s == ST_FOLLOWER);
         }
         nf = __reduce_add_sync(0xffffffffu, nf);
@@ -1154,12 +1236,63 @@ __global__ void __launch_bounds__(128) evac_aux_kernel(const __grid_constant__ K
       } else {
         if (tid == 0) store_head_obs<real>(row, ap.x, ap.y, a);
         for (int i = tid; i < N; i += 128) {
-          const real2 p = a.pos[(size_t)e * N + i];
-          store_ped_obs<real>(row, i, N, p.x, p.y, (int)a.status[(size_t)e * N + i], ap.x, ap.y, a);
+          real px, py, dx, dy;
+          int s;
+          state_load_ped<real>(a, e, i, px, py, dx, dy, s);
+          store_ped_obs<real>(row, i, N, px, py, s, ap.x, ap.y, a);
         }
       }
     }
     __syncthreads();
+  }
+}
+
+// get_state / set_state / get_accumulators of an EnvBlock handle (SoA handles use plain copies): one 64-thread CTA per
+// environment; any array pointer may be NULL.  WRITE = set_state (API arrays -> blocks), else blocks -> API arrays.
+struct StateIO {
+  float2* positions;   // [E,N]
+  float2* directions;  // [E,N]
+  uint8_t* statuses;   // [E,N]
+  float2* agent_position;
+  float2* agent_direction;
+  int* now;            // [E]
+  double* acc;         // [E,3]   (read only)
+  long long* overall;  // [E]     (read only)
+};
+template <bool WRITE>
+__global__ void __launch_bounds__(64) evac_block_io_kernel(unsigned char* __restrict__ blocks, int E, int N, StateIO io) {
+  const int e = blockIdx.x, i = threadIdx.x;
+  if (e >= E) return;
+  unsigned char* b = blocks + (size_t)e * BLK_BYTES;
+  float4* ped = reinterpret_cast<float4*>(b + BLK_PED);
+  EnvRec* rec = reinterpret_cast<EnvRec*>(b);
+  if (i < N) {
+    const size_t g = (size_t)e * N + i;
+    if (WRITE) {
+      float4 v = ped[i];
+      if (io.positions) { const float2 p = io.positions[g]; v.x = p.x; v.y = p.y; }
+      if (io.directions) { const float2 d = io.directions[g]; v.z = d.x; v.w = d.y; }
+      if (io.positions || io.directions) ped[i] = v;
+      if (io.statuses) b[blk_status_off(i)] = io.statuses[g];
+    } else {
+      const float4 v = ped[i];
+      if (io.positions) io.positions[g] = make_float2(v.x, v.y);
+      if (io.directions) io.directions[g] = make_float2(v.z, v.w);
+      if (io.statuses) io.statuses[g] = b[blk_status_off(i)];
+    }
+  }
+  if (i == 0) {
+    if (WRITE) {
+      if (io.agent_position) { rec->agent_pos = io.agent_position[e]; rec->agent_state = 0; }  // a moved agent restarts its script
+      if (io.agent_direction) rec->agent_dir = io.agent_direction[e];
+      if (io.now) rec->now = io.now[e];
+    } else {
+      if (io.agent_position) io.agent_position[e] = rec->agent_pos;
+      if (io.agent_direction) io.agent_direction[e] = rec->agent_dir;
+      if (io.now) io.now[e] = rec->now;
+      if (io.acc) { io.acc[3 * (size_t)e] = rec->acc[0]; io.acc[3 * (size_t)e + 1] = rec->acc[1]; io.acc[3 * (size_t)e + 2] = rec->acc[2]; }
+      if (io.overall) io.overall[e] = rec->overall;
+    }
   }
 }
 

@@ -61,7 +61,13 @@ struct WPed {
 // WPC = environments (independent warps) per CTA: fewer, fatter CTAs for the block scheduler; no block-level barrier anywhere.
 template <int MODE, int WPC>
 __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
-  __shared__ __align__(16) float4 tile_all[WPC][66];  // Tile<float> of 64 slots (+ the look-ahead entries) per warp
+  // Tile<float> of 64 slots (+ the look-ahead entries) per warp = 66 float4.  EVAC_OBS_STAGED (A/B variant): after the pairwise
+  // pass the same memory stages the observation row ((64 + 2) x 6 floats = 99 float4), see the observation section
+#ifdef EVAC_OBS_STAGED
+  __shared__ __align__(16) float4 tile_all[WPC][99];
+#else
+  __shared__ __align__(16) float4 tile_all[WPC][66];
+#endif
   // strip culling (a.cells_x > 0): the sources are sorted by vertical strip (edge >= vision radius) so that a
   // pedestrian only visits the slots of its own and the two adjacent strips
   __shared__ uint2 strip_mask_all[WPC][32];   // per strip: which lanes' pedestrian 0 (.x) / pedestrian 1 (.y) sit in it
@@ -69,6 +75,9 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
   const int wic = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31, e = blockIdx.x * WPC + wic, N = a.N;
   if (e >= a.E) return;
+#ifdef EVAC_PROBE_EMPTY  // measurement variant (never shipped): launch + CTA scheduling cost only
+  if (a.N >= 0) return;
+#endif
   const Tile<float> tile(reinterpret_cast<unsigned char*>(tile_all[wic]), 64);
   uint2* strip_mask = strip_mask_all[wic];
   int* strip_start = strip_start_all[wic];
@@ -78,31 +87,28 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
   const uint32_t env_g = (uint32_t)(a.env_offset + e);
   const float2 exit_p = make_float2(0.f, -1.f);  // area.py:36-39
 
-  // ---------------- load state: everything this launch reads is requested before anything is used
-  float2* __restrict__ pos_e = a.pos + (size_t)e * N;
-  float2* __restrict__ dir_e = a.dir + (size_t)e * N;
-  uint8_t* __restrict__ st_e = a.status + (size_t)e * N;
-  WPed q[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    q[k].p = q[k].d = make_float2(0.f, 0.f);
-    q[k].st = ST_NONE;
-    if (valid[k]) {
-      q[k].p = pos_e[lane + 32 * k];
-      q[k].d = dir_e[lane + 32 * k];
-      q[k].st = st_e[lane + 32 * k];
-    }
-  }
-  float2 ap = a.agent_pos[e], ad = a.agent_dir[e];
-  int wac_state = (a.agent_kind == AGENT_WACUUM) ? a.agent_state[e] : 0;
-  int now = a.now[e];
-  int episode = a.episode[e];
+  // ---------------- load state: everything this launch reads is requested before anything is used.  One address per
+  // environment (EnvBlock, evac_kernels.cuh): the record as two broadcast LDG.128, one LDG.128 per pedestrian
+  // ({px, py, dx, dy}), one LDG.U16 for the lane's two statuses; slots >= N hold zeros / status 0 and are never valid.
+  unsigned char* const blk = a.blocks + (size_t)e * BLK_BYTES;
+  float4* const ped_l = reinterpret_cast<float4*>(blk + BLK_PED) + lane;
+  unsigned short* const st_l = reinterpret_cast<unsigned short*>(blk + BLK_STATUS) + lane;
+  const float4 pd0 = ped_l[0], pd1 = ped_l[32];
+  const unsigned st2 = *st_l;
+  const float4 rec0 = *reinterpret_cast<const float4*>(blk);      // agent_pos, agent_dir
+  const int4 rec1 = *reinterpret_cast<const int4*>(blk + 16);     // now, episode, agent_state
   long long overall = 0;
   double acc_r = 0, acc_i = 0, acc_s = 0;  // lane 0: the episode accumulators of env.py:168-170
   if (lane == 0) {
-    overall = a.overall[e];
-    acc_r = a.acc[3 * (size_t)e]; acc_i = a.acc[3 * (size_t)e + 1]; acc_s = a.acc[3 * (size_t)e + 2];
+    const longlong2 r2 = *reinterpret_cast<const longlong2*>(blk + 32);
+    const double2 r3 = *reinterpret_cast<const double2*>(blk + 48);
+    overall = r2.x; acc_r = __longlong_as_double(r2.y); acc_i = r3.x; acc_s = r3.y;
   }
+  WPed q[2];
+  q[0].p = make_float2(pd0.x, pd0.y); q[0].d = make_float2(pd0.z, pd0.w); q[0].st = (int)(st2 & 0xffu);
+  q[1].p = make_float2(pd1.x, pd1.y); q[1].d = make_float2(pd1.z, pd1.w); q[1].st = (int)(st2 >> 8);
+  float2 ap = make_float2(rec0.x, rec0.y), ad = make_float2(rec0.z, rec0.w);
+  int now = rec1.x, episode = rec1.y, wac_state = rec1.z;
   float reward_sum = 0.f;
   int any_term = 0, any_trunc = 0;
   const float noise_c = a.noise_coef;
@@ -111,6 +117,12 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
   const float2 wall = make_float2(a.width, a.height);
 
   for (int s = 0; s < a.num_steps; ++s) {  // @region wrng
+#ifdef EVAC_PROBE_FLOOR  // measurement variant (never shipped): load -> observation -> write back, no dynamics
+    float2 act_tbl = make_float2(0.f, 0.f);
+    if (a.agent_kind == AGENT_TABLE) act_tbl = a.actions[(size_t)s * a.E + e];
+    ap.x += 1e-9f * act_tbl.x;
+    reward_sum += act_tbl.y;
+#else
     // ---------------- Time.step [area.py:53-59]
     const int now_prev = now;
     now += 1;
@@ -230,8 +242,12 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
       for (int k = 0; k < 2; ++k) windowed_pass(tile, win_lo[k], win_hi[k], q[k].p.x, q[k].p.y, a.thr2_ped, sx[k], sy[k]);
     } else {
       const float xi[2] = {q[0].p.x, q[1].p.x}, yi[2] = {q[0].p.y, q[1].p.y};
+#ifdef EVAC_PROBE_NOPAIR  // measurement variant (never shipped): the step without its pairwise pass
+      sx[0] = sx[1] = q[0].d.x; sy[0] = sy[1] = q[1].d.y;
+#else
       if (__any_sync(0xffffffffu, fv[0] | fv[1])) pairwise_pass<2, false, EVAC_PAIR_UNROLL>(tile, n_src, xi, yi, a.thr2_ped, sx, sy, cnt);
       else sx[0] = sx[1] = sy[0] = sy[1] = 0.f;
+#endif
     }
     // ---------------- new headings, enslaving, integration, reflection, statuses  // @region wupdate
     const float2 e_ad = make_float2(__fmul_rn(a.enslaving_f, ad.x), __fmul_rn(a.enslaving_f, ad.y));  // float32 like area.py:140
@@ -321,29 +337,72 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
         }
       }
     }
+#endif  // EVAC_PROBE_FLOOR
     // ---------------- observation [wrappers.py:8-96, gravity_encoding.py:8-81]  // @region wobs
+#if defined(EVAC_PROBE_NOOBS)
+    if (false) {
+#else
     if (obs_e != nullptr && (a.obs_every_step || s == a.num_steps - 1)) {
+#endif
       float* row = obs_e + (a.obs_every_step ? (size_t)s * a.E * a.obs_dim : (size_t)0);
       if constexpr (MODE == WMODE_REL_OHE_BOX) {
-        // rows = [agent; exit; pedestrians], cols = [x, y, ohe(4)]; relative positions / sqrt(2) (float32 hypotenuse)
+        // rows = [agent; exit; pedestrians], cols = [x, y, ohe(4)]; relative positions / sqrt(2) (float32 hypotenuse).
+        // Default: three float2 stores per pedestrian straight from registers (24-byte row stride: a warp's STG.64 touches 24
+        // sectors for 256 useful bytes, the sectors are completed in L2 by the neighbouring lanes' stores).
+        // EVAC_OBS_STAGED: the row is assembled in shared memory and copied out with one 16-byte (N even) or 8-byte store per
+        // lane and round -- 512 contiguous bytes per warp instruction.  Measured on B200, same box, 4096 x 60 per-step regime:
+        // the load -> observe -> write-back skeleton gets faster (5.23 -> 4.82 us) but the FULL step slower (8.42 -> 8.66 us:
+        // STS -> LDS -> STG adds a dependent shared-memory round trip to every warp's tail), so the direct stores stay.
         const float inv_hyp = (float)(1.0 / 1.41421353816986083984375);
         const float2 nap = make_float2(-ap.x, -ap.y);
+#ifndef EVAC_OBS_STAGED
         if (lane == 0) {
           const float2 ex = __fmul2_rn(__fadd2_rn(exit_p, nap), splat(inv_hyp));
-          float2* r = reinterpret_cast<float2*>(row);  // rows of 24 (N + 2) bytes: 8-byte aligned for every N
-          r[0] = ap; r[1] = make_float2(0.f, 0.f); r[2] = make_float2(0.f, 0.f);  // agent row, status [0,0,0,0]
-          r[3] = ex; r[4] = make_float2(1.f, 0.f); r[5] = make_float2(0.f, 0.f);  // exit row,  status [1,0,0,0]
+          float2* r = reinterpret_cast<float2*>(row);
+          r[0] = ap; r[1] = make_float2(0.f, 0.f); r[2] = make_float2(0.f, 0.f);
+          r[3] = ex; r[4] = make_float2(1.f, 0.f); r[5] = make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           if (valid[k]) {
             float2* r = reinterpret_cast<float2*>(row + (lane + 32 * k + 2) * 6);
+            const int st = q[k].st;
+            r[0] = __fmul2_rn(__fadd2_rn(q[k].p, nap), splat(inv_hyp));
+            r[1] = make_float2(st == ST_ESCAPED ? 1.f : 0.f, st == ST_EXITING ? 1.f : 0.f);
+            r[2] = make_float2(st == ST_FOLLOWER ? 1.f : 0.f, st == ST_VISCEK ? 1.f : 0.f);
+          }
+        }
+#else
+        float2* stage = reinterpret_cast<float2*>(tile_all[wic]);
+        if (lane == 0) {
+          const float2 ex = __fmul2_rn(__fadd2_rn(exit_p, nap), splat(inv_hyp));
+          stage[0] = ap; stage[1] = make_float2(0.f, 0.f); stage[2] = make_float2(0.f, 0.f);  // agent row, status [0,0,0,0]
+          stage[3] = ex; stage[4] = make_float2(1.f, 0.f); stage[5] = make_float2(0.f, 0.f);  // exit row,  status [1,0,0,0]
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (valid[k]) {
+            float2* r = stage + (lane + 32 * k + 2) * 3;
             const int st = q[k].st;  // column 4 - status: ESCAPED -> 0, EXITING -> 1, FOLLOWER -> 2, VISCEK -> 3
             r[0] = __fmul2_rn(__fadd2_rn(q[k].p, nap), splat(inv_hyp));
             r[1] = make_float2(st == ST_ESCAPED ? 1.f : 0.f, st == ST_EXITING ? 1.f : 0.f);
             r[2] = make_float2(st == ST_FOLLOWER ? 1.f : 0.f, st == ST_VISCEK ? 1.f : 0.f);
           }
         }
+        __syncwarp();
+        if ((N & 1) == 0) {
+          const int n16 = (N + 2) * 3 / 2;  // float4 chunks of the row
+          const float4* src = tile_all[wic];
+          float4* dst = reinterpret_cast<float4*>(row);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { const int j = lane + 32 * c; if (j < n16) dst[j] = src[j]; }
+        } else {
+          const int n8 = (N + 2) * 3;
+          float2* dst = reinterpret_cast<float2*>(row);
+#pragma unroll
+          for (int c = 0; c < 7; ++c) { const int j = lane + 32 * c; if (j < n8) dst[j] = stage[j]; }
+        }
+#endif
       } else if (MODE == WMODE_GRAV || a.positions == POS_GRAV) {
         float gx = 0.f, gy = 0.f;
         int nf = 0;
@@ -366,19 +425,24 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
   }  // steps
 
   // ---------------- write back  // @region wwriteback
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    if (valid[k]) {
-      pos_e[lane + 32 * k] = q[k].p;
-      dir_e[lane + 32 * k] = q[k].d;
-      st_e[lane + 32 * k] = (uint8_t)q[k].st;
-    }
+#if defined(EVAC_PROBE_NOSTATE)
+  if (q[0].p.x == 123.456f)
+#endif
+  {
+    ped_l[0] = make_float4(q[0].p.x, q[0].p.y, q[0].d.x, q[0].d.y);
+    ped_l[32] = make_float4(q[1].p.x, q[1].p.y, q[1].d.x, q[1].d.y);
+    *st_l = (unsigned short)(q[0].st | (q[1].st << 8));
+  }
+  if (a.status_out != nullptr) {  // host face: dense [E,N] statuses travel in the result block
+    uint8_t* so = a.status_out + (size_t)e * N + lane;
+    if (valid[0]) so[0] = (uint8_t)q[0].st;
+    if (valid[1]) so[32] = (uint8_t)q[1].st;
   }
   if (lane == 0) {
-    a.agent_pos[e] = ap; a.agent_dir[e] = ad;
-    if (a.agent_kind == AGENT_WACUUM) a.agent_state[e] = wac_state;
-    a.now[e] = now; a.episode[e] = episode; a.overall[e] = overall;
-    a.acc[3 * (size_t)e] = acc_r; a.acc[3 * (size_t)e + 1] = acc_i; a.acc[3 * (size_t)e + 2] = acc_s;
+    *reinterpret_cast<float4*>(blk) = make_float4(ap.x, ap.y, ad.x, ad.y);
+    *reinterpret_cast<int4*>(blk + 16) = make_int4(now, episode, wac_state, 0);
+    *reinterpret_cast<longlong2*>(blk + 32) = make_longlong2(overall, __double_as_longlong(acc_r));
+    *reinterpret_cast<double2*>(blk + 48) = make_double2(acc_i, acc_s);
     if (a.reward) a.reward[e] = reward_sum;
     if (a.terminated) a.terminated[e] = (uint8_t)any_term;
     if (a.truncated) a.truncated[e] = (uint8_t)any_trunc;

@@ -73,10 +73,17 @@ class _Pedestrians:
     @property
     def statuses(self):
         """uint8 codes with the reference's enum values (Status.X.value)."""
+        env = self._env
+        if not env.batched and env._host_statuses is not None:  # came back with the last step's result block
+            return np.array(env._host_statuses[0], dtype=np.uint8)
         return self._fetch("statuses")
 
     @property
     def status_stats(self):  # pedestrians.py:37-44
+        env = self._env
+        if not env.batched and env._host_statuses is not None:
+            h = env._host_statuses[0]
+            return {k: int(np.count_nonzero(h == v)) for k, v in (("escaped", 4), ("exiting", 3), ("following", 2), ("viscek", 1))}
         s = self._env.get_state()["statuses"]
         out = {k: (s == v).sum(dim=1) for k, v in
                (("escaped", 4), ("exiting", 3), ("following", 2), ("viscek", 1))}
@@ -439,16 +446,16 @@ class EvacuationEnv:
             self.pedestrians.save()
         return self._emit_obs(), {}
 
-    def _numpy_noise(self):
+    def _numpy_noise(self, out=None):
         """area.py:124: one U(-c/2, c/2) draw per VISCEK/FOLLOWER pedestrian, ascending index, from
         the global NumPy stream; scattered into the dense [E,N] table the kernel consumes."""
         E, N, c = self.num_envs, self.cfg.number_of_pedestrians, self.cfg.noise_coef
         if self._host_statuses is None:
             self._host_statuses = self.get_state()["statuses"].cpu().numpy()
-        noise = np.zeros((E, N), dtype=np.float32)
+        noise = np.zeros((E, N), dtype=np.float32) if out is None else out
         for e in range(E):
-            fv = (self._host_statuses[e] == 1) | (self._host_statuses[e] == 2)
-            noise[e, fv] = np.random.uniform(low=-c / 2, high=c / 2, size=int(fv.sum()))
+            fv = self._host_statuses[e] <= 2  # VISCEK = 1, FOLLOWER = 2 (statuses are 1..4)
+            noise[e, fv] = np.random.uniform(low=-c / 2, high=c / 2, size=int(np.count_nonzero(fv)))
         return noise
 
     def step(self, action, noise=None):
@@ -478,33 +485,43 @@ class EvacuationEnv:
                 self.agent.save()
             return (self._obs_view, self._reward, self._terminated_b, self._truncated_b, {})
         # ---- single-env face: host buffers through evac_step_host
-        if noise is None and self.rng == "numpy":
-            noise = self._numpy_noise()
-        nz = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float32).reshape(E, N))
         if self._host is None:
-            # ONE page-locked block [obs | reward | terminated | truncated]: evac_step_host fills it with a single D2H copy;
-            # the actions are staged in a page-locked array too, so the library copies straight from it.  Pointers are
-            # taken once (ctypes / data_ptr conversions are a measurable part of a 150 us step).
+            # ONE page-locked block [obs | reward | terminated | truncated | statuses]: evac_step_host fills it with a single
+            # D2H copy; the actions (and the injected noise) are staged in page-locked arrays too, so the library copies straight
+            # from them.  Pointers are taken once (ctypes / data_ptr conversions are a measurable part of a step).
             D = self.obs_dim
-            blk = torch.empty(E * D * 4 + E * 4 + 2 * E, dtype=torch.uint8, pin_memory=True)
-            o0, r0, t0 = E * D * 4, E * D * 4 + E * 4, E * D * 4 + E * 4 + E
+            blk = torch.empty(E * D * 4 + E * 4 + 2 * E + E * N, dtype=torch.uint8, pin_memory=True)
+            o0, r0, t0, s0 = E * D * 4, E * D * 4 + E * 4, E * D * 4 + E * 4 + E, E * D * 4 + E * 4 + 2 * E
             self._host_block = blk
-            self._host = dict(obs=blk[:o0].view(torch.float32).view(E, D), rew=blk[o0:r0].view(torch.float32), term=blk[r0:t0], trunc=blk[t0:])
+            self._host = dict(obs=blk[:o0].view(torch.float32).view(E, D), rew=blk[o0:r0].view(torch.float32), term=blk[r0:t0], trunc=blk[t0:s0],
+                              status=blk[s0:].view(E, N))
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
             self._host_np["term_b"], self._host_np["trunc_b"] = self._host_np["term"].view(np.bool_), self._host_np["trunc"].view(np.bool_)
             self._act_pin = torch.empty((E, 2), dtype=torch.float32, pin_memory=True)
             self._act_np = self._act_pin.numpy()
-            self._host_ptrs = tuple(_ptr(t) for t in (self._act_pin, self._host["obs"], self._host["rew"], self._host["term"], self._host["trunc"]))
+            self._noise_pin = torch.empty((E, N), dtype=torch.float32, pin_memory=True)
+            self._noise_np = self._noise_pin.numpy()
+            self._host_ptrs = tuple(_ptr(t) for t in (self._act_pin, self._host["obs"], self._host["rew"], self._host["term"], self._host["trunc"],
+                                                      self._host["status"], self._noise_pin))
         self._act_np[...] = np.asarray(action, dtype=np.float32).reshape(E, 2)
+        if noise is None and self.rng == "numpy":
+            noise = self._numpy_noise(out=self._noise_np)
+        pn = None
+        if noise is not None:
+            if noise is not self._noise_np:
+                self._noise_np[...] = np.asarray(noise, dtype=np.float32).reshape(E, N)
+            pn = self._host_ptrs[6]
         # outputs alias the page-locked buffers and are valid until the next step (the reference's
         # observations alias live state in the same way, env.py:100-102)
         hn = self._host_np
         obs, rew, term, trunc = hn["obs"], hn["rew"], hn["term"], hn["trunc"]
         torch.cuda.current_stream(self.device).synchronize()
-        pa, po, pr, pt, pu = self._host_ptrs
-        nat.check(lib.evac_step_host(h, pa, None if nz is None else nz.ctypes.data_as(C.c_void_p), po, pr, pt, pu))
-        if self.rng == "numpy":
-            self._host_statuses = self.get_state()["statuses"].cpu().numpy()
+        pa, po, pr, pt, pu, ps = self._host_ptrs[:6]
+        want_statuses = self.rng == "numpy" or E == 1  # (a large Philox batch does not pay the extra N bytes per env)
+        nat.check(lib.evac_step_host(h, pa, pn, po, pr, pt, pu, ps if want_statuses else None))
+        # the statuses after the step came back in the same copy (no get_state round trip): the next step's noise draw
+        # (area.py:124: one value per VISCEK / FOLLOWER pedestrian) and `pedestrians.statuses` read them from here
+        self._host_statuses = hn["status"] if want_statuses else None
         if self.draw:
             self.pedestrians.save()
             self.agent.save()

@@ -363,6 +363,7 @@ class PolicyRollout:
         self.out = {k: torch.zeros(s, device=self.device) for k, s in
                     (("action", (self.E, 2)), ("logprob", (self.E,)), ("value", (self.E,)), ("reward", (self.E,)))}
         self._graph = None
+        self.launches_per_iteration = None
         # fused policy: NormalizeObservation runs in the prologue of the policy kernel on the env's raw observation buffer,
         # so `next_obs` (the normalised observation the policy saw) is produced INSIDE the iteration
         self.fused = isinstance(policy, FusedRPOTransformerPolicy)
@@ -404,8 +405,13 @@ class PolicyRollout:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self._graph = torch.cuda.CUDAGraph()
+        count = lambda: self.env.unwrapped.launch_count + (self.policy.launch_count if self.fused else 0)
+        before = count()
         with torch.cuda.graph(self._graph):
             self._iteration()
+        # kernels of THIS library recorded into one graph replay: the handles count launches at capture time; the fused loop's
+        # evac_normalize_reward is a handle-less entry point (+1)
+        self.launches_per_iteration = count() - before + (1 if self.fused else 0)
 
     def run(self, num_steps: int):
         """Returns the storage dict ([T, E, ...]) when `store`, else None."""

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define EVAC_ABI_VERSION 4
+#define EVAC_ABI_VERSION 5
 
 enum {
   EVAC_OK = 0,
@@ -169,9 +169,13 @@ int evac_step(EvacHandle* h, const float* actions, const float* noise, float* ob
 
 /* Same call with HOST buffers: copies actions (and noise) host->device, steps, copies
  * obs / reward / flags device->host through the handle's pinned staging buffers and
- * synchronises.  This is the call a host-side Gymnasium user makes once per step. */
+ * synchronises.  This is the call a host-side Gymnasium user makes once per step.
+ *   statuses   [E,N] uint8 out or NULL: the pedestrian statuses after the step (env.unwrapped.pedestrians.statuses,
+ *              pedestrians.py:12; the rng="numpy" face needs them to draw the next step's |viscek + follower| noise
+ *              values, area.py:124).  When obs, reward, terminated, truncated, statuses are page-locked and laid out back
+ *              to back in that order, the whole result travels in ONE device->host copy. */
 int evac_step_host(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward,
-                   uint8_t* terminated, uint8_t* truncated);
+                   uint8_t* terminated, uint8_t* truncated, uint8_t* statuses);
 
 /* `num_steps` consecutive steps in ONE kernel launch with the state kept on chip.
  *   agent_kind EVAC_AGENT_TABLE: actions [num_steps,E,2] float32; EVAC_AGENT_RANDOM: U[-1,1)^2

@@ -155,8 +155,8 @@ def _record_summary(kind, name, summary):
 # those may reach FREE_DIR_CAP and must stay a small fraction of all entries.  Values set from the recorded summaries
 # (profiles/r02*/parity/): see DESIGN.md section 4.
 FREE_POS_RTOL = 1e-5
-FREE_DIR_CAP = 2e-3
-FREE_DIR_FRAC = 2e-3
+FREE_DIR_CAP = 2e-4   # observed (profiles/r02a/parity): worst 6.7e-5 of a step, on an ill-conditioned heading
+FREE_DIR_FRAC = 2e-3  # observed: at most 7.5e-4 of the entries above 1e-5
 
 
 @pytest.mark.parametrize("name", ["c2_rel_ohe_box_seed0", "c2_rel_ohe_box_seed3", "c3_grav_a3", "c1_default_seed0", "c1_default_seed1",
@@ -165,7 +165,7 @@ def test_free_running_episode_parity(name):
     """Free-running episode (up to 2000 steps): the kernel carries its own float32 state, the oracle its float64 state;
     same actions and injected noise; the kernel state is NEVER re-synchronised because of numerical error -- only when a
     thresholded decision flips at a step whose oracle margin is below the accumulated float32 drift (a status / neighbour
-    set that legitimately differs; at most 3 per episode, each asserted to be a near-threshold step).  Everything observed
+    set that legitimately differs; at most 1 per episode, asserted to be a near-threshold step; none observed so far).  Everything observed
     is recorded (resyncs, ill-conditioned steps, worst errors and when) in gpurun_out/parity/."""
     case, z = T.load_golden(name)
     rec = _run_oracle_episode(case, z)
@@ -214,10 +214,10 @@ def test_free_running_episode_parity(name):
         dir_entries_above_1e5=float((dir_err[ok] > 1e-5).mean()) if ok.any() else 0.0,
         pos_steps_above_1e5=int((pos_step > 1e-5).sum()),
         worst_pos_up_to={str(m): float(pos_step[:m].max()) for m in marks}, worst_dir_up_to={str(m): float(dir_step[:m].max()) for m in marks},
-        bars=dict(pos=FREE_POS_RTOL, dir_cap=FREE_DIR_CAP, dir_frac=FREE_DIR_FRAC, max_status_resyncs=3))
+        bars=dict(pos=FREE_POS_RTOL, dir_cap=FREE_DIR_CAP, dir_frac=FREE_DIR_FRAC, max_status_resyncs=1))
     _record_summary("free_running", name, summary)
     print(f"[{name}] {summary}")
-    assert len(resync_steps) <= 3, f"{len(resync_steps)} near-threshold re-synchronisations in {steps} steps"
+    assert len(resync_steps) <= 1, f"{len(resync_steps)} near-threshold re-synchronisations in {steps} steps"  # observed: 0 on every golden
     assert pos_step.max() <= FREE_POS_RTOL, f"positions: max rel err {pos_step.max():.3e} at step {pos_step.argmax()}"
     assert rew_err.max() <= FREE_POS_RTOL, f"reward: max rel err {rew_err.max():.3e}"
     assert dir_step.max() <= FREE_DIR_CAP, f"directions: max err {dir_step.max():.3e} of a step at step {dir_step.argmax()}"
@@ -437,7 +437,7 @@ def test_cluster_pass_is_bit_identical_across_cluster_sizes(n, vision, monkeypat
         for k in ("pos", "dir", "st"):  # against the one-CTA kernel: the state bit for bit ...
             assert np.array_equal(out["1"][k], out["2"][k], equal_nan=True), (wrap, k)
         for k in ("rew", "obs"):  # ... sums over ALL pedestrians (intrinsic reward, gravity observation) group the float32 partials differently
-            np.testing.assert_allclose(out["2"][k], out["1"][k], rtol=2e-6, atol=1e-6, err_msg=str((wrap, k)))
+            np.testing.assert_allclose(out["2"][k], out["1"][k], rtol=1e-5, atol=1e-6, err_msg=str((wrap, k)))
 
 
 @pytest.mark.parametrize("n,cluster", [(16384, "4"), (16384, "8"), (32768, "8"), (32768, "4")])

@@ -295,13 +295,22 @@ def test_header_is_plain_c_and_the_library_is_a_c_abi():
         assert int(n) == 10 and float(to_exit) == 0.4 and int(version) >= 1
 
 
-def test_bench_reference_arm_prints_one_contract_line():
-    """`bench.py --impl reference` (the reference algorithm on the host cores; runs without a GPU): exactly one JSON line on
-    stdout with the driver's keys, `impl`, a `cpu_baseline` describing the run and an `e2e` equal to the line's value."""
+@pytest.mark.parametrize("force_port", [False, True])
+def test_bench_reference_arm_prints_one_contract_line(force_port):
+    """`bench.py --impl reference` (the reference's CPU step loop on the host cores; runs without a GPU): exactly one JSON line
+    on stdout with the driver's keys, `impl`, a `cpu_baseline` describing the run and an `e2e` equal to the line's value.
+    kind = "reference" (the unmodified reference through oracle/ref_shim.py) wherever a copy is reachable -- /root/reference
+    here, baseline/_ref on the GPU box -- else "port" (the oracle)."""
     import json
 
+    from oracle import ref_shim
+
+    env = dict(os.environ, EVAC_BENCH_MIN_SECONDS="1")
+    if force_port:
+        env["EVAC_BENCH_CPU_KIND"] = "port"
+    want_kind = "port" if force_port or not ref_shim.reference_available() else "reference"
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0, res.stderr
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -311,7 +320,7 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["steps"] == 3 and d["warmup"] == 1 and d["higher_is_better"] is True
     assert d["unit"] == "pedestrian-steps/s" and d["value"] > 0 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

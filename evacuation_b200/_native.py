@@ -89,6 +89,9 @@ SIGNATURES = {
     "evac_episode_stats": (C.c_int, [_P, _P, _P, _P, _P]),
     "evac_get_accumulators": (C.c_int, [_P, _P, _P, _P]),
     "evac_launch_count": (C.c_int64, [_P]),
+    "evac_state_bytes": (C.c_int64, [_P]),
+    "evac_save_state": (C.c_int, [_P, _P, _P]),
+    "evac_load_state": (C.c_int, [_P, _P, _P]),
     "evac_policy_default_config": (C.c_int, [C.POINTER(EvacPolicyConfig), C.c_int32, C.c_int32]),
     "evac_policy_create": (C.c_int, [C.POINTER(EvacPolicyConfig), C.c_int32, C.POINTER(_P)]),
     "evac_policy_destroy": (C.c_int, [_P]),

@@ -152,6 +152,8 @@ static int launch_step_t(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
   auto kern = evac_step_kernel<real, THREADS, PPT>;
   if (smem > 48 * 1024 && attr_set[h->device & 15] < smem) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the whole unified L1 / shared-memory array as shared memory: lets two 113 KB CTAs of the 512 x 8 shape share an SM
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     attr_set[h->device & 15] = smem;
   }
   kern<<<a.E, THREADS, smem, st>>>(a);
@@ -197,7 +199,12 @@ static void pick_shape(int n, int* threads, int* ppt) {
   else if (n <= 512) { *threads = 256; *ppt = 2; }
   else if (n <= 1024) { *threads = 512; *ppt = 2; }
   else if (n <= 2048) { *threads = 512; *ppt = 4; }
-  else if (n <= 4096) { *threads = 1024; *ppt = 4; }
+  else if (n <= 4096) {
+    // 1024 x 4 = one CTA per SM; EVAC_SHAPE_4096=512x8: two co-resident CTAs per SM (113 KB of shared memory each, 64 registers):
+    // 256 environments are then ONE wave on 148 SMs instead of 1.73, and a CTA's barrier stalls are filled by its neighbour
+    const char* s4 = getenv("EVAC_SHAPE_4096");
+    if (s4 && strcmp(s4, "512x8") == 0) { *threads = 512; *ppt = 8; } else { *threads = 1024; *ppt = 4; }
+  }
   else { *threads = 1024; *ppt = 8; }  // up to 8192: the sorted tile (16 B per pedestrian) + cell list still fit one SM's shared memory
 }
 
@@ -240,6 +247,9 @@ static int launch_step(EvacHandle* h, const KArgs<real>& a, cudaStream_t st) {
     case 256 * 16 + 2: return launch_step_t<real, 256, 2>(h, a, st);
     case 512 * 16 + 2: return launch_step_t<real, 512, 2>(h, a, st);
     case 512 * 16 + 4: return launch_step_t<real, 512, 4>(h, a, st);
+    case 512 * 16 + 8:
+      if constexpr (std::is_same<real, float>::value) return launch_step_t<real, 512, 8>(h, a, st);
+      break;
     case 1024 * 16 + 4: return launch_step_t<real, 1024, 4>(h, a, st);
     case 1024 * 16 + 8:
       if constexpr (std::is_same<real, float>::value) return launch_step_t<real, 1024, 8>(h, a, st);
@@ -600,6 +610,56 @@ int evac_get_accumulators(EvacHandle* h, double* acc, int64_t* overall_timesteps
   return EVAC_OK;
 }
 
+// ---- checkpoint / resume: the COMPLETE device state of a handle as one flat byte image
+struct StateRegion { void* ptr; size_t bytes; };
+static int state_regions(EvacHandle* h, StateRegion* r) {
+  const size_t E = h->E, en = (size_t)h->E * h->N, es = h->prec == EVAC_PREC_F64 ? 16 : 8;
+  int n = 0;
+  if (h->blocks) {
+    r[n++] = {h->blocks, E * BLK_BYTES};
+  } else {
+    r[n++] = {h->pos, en * es}; r[n++] = {h->dir, en * es}; r[n++] = {h->status, en};
+    r[n++] = {h->agent_pos, E * 8}; r[n++] = {h->agent_dir, E * 8}; r[n++] = {h->now, E * 4}; r[n++] = {h->episode, E * 4};
+    r[n++] = {h->overall, E * 8}; r[n++] = {h->acc, E * 24}; r[n++] = {h->agent_state, E * 4};
+  }
+  r[n++] = {h->ep_stats, E * EVAC_NUM_EPISODE_STATS * 4}; r[n++] = {h->ep_finished, E};
+  r[n++] = {h->totals, (1 + EVAC_NUM_EPISODE_STATS) * 8};
+  return n;
+}
+
+int64_t evac_state_bytes(EvacHandle* h) {
+  if (!h) return -1;
+  StateRegion r[16];
+  const int n = state_regions(h, r);
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) total += (r[i].bytes + 15) & ~(size_t)15;
+  return (int64_t)total;
+}
+
+static int state_copy(EvacHandle* h, unsigned char* image, bool save, cudaStream_t st) {
+  StateRegion r[16];
+  const int n = state_regions(h, r);
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    if (save) CK(cudaMemcpyAsync(image + off, r[i].ptr, r[i].bytes, cudaMemcpyDeviceToDevice, st));
+    else CK(cudaMemcpyAsync(r[i].ptr, image + off, r[i].bytes, cudaMemcpyDeviceToDevice, st));
+    off += (r[i].bytes + 15) & ~(size_t)15;
+  }
+  return EVAC_OK;
+}
+
+int evac_save_state(EvacHandle* h, void* image, void* stream) {
+  if (!h || !image) return fail(EVAC_ERR_INVALID, "NULL argument");
+  if (int r = set_device(h)) return r;
+  return state_copy(h, (unsigned char*)image, true, (cudaStream_t)stream);
+}
+
+int evac_load_state(EvacHandle* h, const void* image, void* stream) {
+  if (!h || !image) return fail(EVAC_ERR_INVALID, "NULL argument");
+  if (int r = set_device(h)) return r;
+  return state_copy(h, (unsigned char*)image, false, (cudaStream_t)stream);
+}
+
 int evac_episode_stats(EvacHandle* h, float* stats, uint8_t* finished, double* totals, void* stream) {
   if (!h) return fail(EVAC_ERR_INVALID, "NULL handle");
   if (int r = set_device(h)) return r;
@@ -650,13 +710,17 @@ __global__ void __launch_bounds__(256) probe_fma_kernel(float* out, int iters, f
 }
 
 // Standalone launch of the SAME pairwise_pass device function the fused step kernel uses, on the same
-// CTA shapes (one environment per CTA; THREADS x PPT = 32x2 or 64x1).
-template <int THREADS, int PPT, int UNR = 4>
-__global__ void __launch_bounds__(THREADS) probe_pairwise_kernel(const float2* __restrict__ pos, const float2* __restrict__ unit,
-                                                                 float2* __restrict__ out, int N, int reps, float thr2) {
+// warp shapes (one environment per warp, THREADS x PPT = 32x2, or one per 64-thread CTA as 64x1).  WPC = environments
+// (independent warps, each with its own tile) per CTA: one-warp CTAs cap an SM at 32 resident warps (the CTA limit);
+// WPC = 2 with 48 registers reaches 40.
+template <int THREADS, int PPT, int UNR = 4, int WPC = 1, int MINB = 1>
+__global__ void __launch_bounds__(THREADS * WPC, MINB) probe_pairwise_kernel(const float2* __restrict__ pos, const float2* __restrict__ unit,
+                                                                             float2* __restrict__ out, int N, int reps, float thr2, int E) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Tile<float> tile(smem_raw, THREADS * PPT);
-  const int tid = threadIdx.x, e = blockIdx.x;
+  const int wic = threadIdx.x / THREADS;
+  Tile<float> tile(smem_raw + (size_t)wic * Tile<float>::bytes(THREADS * PPT), THREADS * PPT);
+  const int tid = threadIdx.x % THREADS, e = blockIdx.x * WPC + wic;
+  if (e >= E) return;
   float xi[PPT], yi[PPT], sx[PPT], sy[PPT], cnt[PPT], accx[PPT], accy[PPT];
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
@@ -666,7 +730,7 @@ __global__ void __launch_bounds__(THREADS) probe_pairwise_kernel(const float2* _
     tile.put(i, p.x, p.y, u.x, u.y);
     xi[k] = p.x; yi[k] = p.y; accx[k] = accy[k] = 0.f;
   }
-  __syncthreads();
+  if (THREADS == 32) __syncwarp(); else __syncthreads();
   for (int r = 0; r < reps; ++r) {
     pairwise_pass<PPT, false, UNR>(tile, N, xi, yi, thr2, sx, sy, cnt);
 #pragma unroll
@@ -828,12 +892,17 @@ int evac_probe_pairwise(int32_t device, int32_t num_envs, int32_t n, int32_t rep
   const bool shape_32x2 = !(shape && strcmp(shape, "64x1") == 0);
   const char* unr_s = getenv("EVAC_PROBE_UNROLL");  // A/B: unroll factor of the slot-pair loop (2 | 4 | 8)
   const int unr = unr_s ? atoi(unr_s) : 4;
+  const char* wpc_s = getenv("EVAC_PROBE_WPC");     // A/B: environments (warps) per CTA of the 32x2 shape: 1 (default) | 2 | 4
+  const int wpc = wpc_s ? atoi(wpc_s) : 1;
+  const size_t tb = Tile<float>::bytes(64);
   for (int rep = 0; rep < 2; ++rep) {
     CK(cudaEventRecord(e0));
-    if (shape_32x2 && unr == 8) probe_pairwise_kernel<32, 2, 8><<<num_envs, 32, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
-    else if (shape_32x2 && unr == 2) probe_pairwise_kernel<32, 2, 2><<<num_envs, 32, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
-    else if (shape_32x2) probe_pairwise_kernel<32, 2><<<num_envs, 32, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
-    else probe_pairwise_kernel<64, 1><<<num_envs, 64, Tile<float>::bytes(64)>>>(pos, unit, out, n, reps, thr2);
+    if (shape_32x2 && wpc == 2) probe_pairwise_kernel<32, 2, 4, 2, 20><<<(num_envs + 1) / 2, 64, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    else if (shape_32x2 && wpc == 4) probe_pairwise_kernel<32, 2, 4, 4, 10><<<(num_envs + 3) / 4, 128, 4 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    else if (shape_32x2 && unr == 8) probe_pairwise_kernel<32, 2, 8><<<num_envs, 32, tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    else if (shape_32x2 && unr == 2) probe_pairwise_kernel<32, 2, 2><<<num_envs, 32, tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    else if (shape_32x2) probe_pairwise_kernel<32, 2><<<num_envs, 32, tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    else probe_pairwise_kernel<64, 1><<<num_envs, 64, tb>>>(pos, unit, out, n, reps, thr2, num_envs);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
   }

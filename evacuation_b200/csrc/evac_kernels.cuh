@@ -830,7 +830,7 @@ __device__ __forceinline__ void random_layout(uint64_t seed, uint32_t env, uint3
 // CL > 1: ONE environment per thread-block cluster of CL CTAs (evac_cluster.cuh) -- CTA r owns pedestrians
 // [r * SLOTS, (r + 1) * SLOTS); float32 + cell list only; per-environment scalars are written by CTA 0.
 template <typename real, int THREADS, int PPT, int CL = 1>  // @region load
-__global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 ? 16 : 1))) evac_step_kernel(const __grid_constant__ KArgs<real> a) {
+__global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 ? 16 : (THREADS == 512 && PPT == 8 ? 2 : 1)))) evac_step_kernel(const __grid_constant__ KArgs<real> a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int SLOTS = THREADS * PPT;
   constexpr bool F64 = std::is_same<real, double>::value;

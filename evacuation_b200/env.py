@@ -337,6 +337,24 @@ class EvacuationEnv:
         nat.check(lib.evac_set_state(h, _ptr(p), _ptr(d), _ptr(s), _ptr(ap), _ptr(ad), _ptr(nw), self._stream()))
         self._host_statuses = None
 
+    def save_state(self) -> torch.Tensor:
+        """Checkpoint: the complete device state of the batch (pedestrians, agent, time, episode indices, accumulators,
+        scripted-agent state, finished-episode statistics) as one uint8 tensor on the env's device.  `load_state(image)` on
+        an env created with the same configuration / num_envs / seed resumes bit-identically (Philox streams are
+        counter-based); `torch.save(image.cpu(), path)` makes it a file."""
+        h, lib = self._handle(), nat.load()
+        image = torch.empty(int(lib.evac_state_bytes(h)), dtype=torch.uint8, device=self.device)
+        nat.check(lib.evac_save_state(h, _ptr(image), self._stream()))
+        return image
+
+    def load_state(self, image: torch.Tensor) -> None:
+        h, lib = self._handle(), nat.load()
+        image = torch.as_tensor(image).to(device=self.device, dtype=torch.uint8).contiguous()
+        if image.numel() != int(lib.evac_state_bytes(h)):
+            raise ValueError(f"state image has {image.numel()} bytes, this environment needs {int(lib.evac_state_bytes(h))}")
+        nat.check(lib.evac_load_state(h, _ptr(image), self._stream()))
+        self._host_statuses = None
+
     def accumulators(self):
         """(acc [E,3] float64: episode_reward, episode_intrinsic_reward, episode_status_reward; overall_timesteps [E] int64)
         of the running episodes (env.py:65-67,168-170)."""

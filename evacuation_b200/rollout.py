@@ -396,11 +396,32 @@ class PolicyRollout:
         self.next_obs.copy_(self.norm.observation(obs.reshape(self.E, self.D)))
         self.next_done.copy_(torch.logical_or(term, trunc).to(self.next_done.dtype))
 
+    def _snapshot(self):
+        """Everything one `_iteration()` mutates: env state (checkpoint image), normaliser statistics, the loop's carried
+        tensors, the policy's stream offset and the observation buffer."""
+        u = self.env.unwrapped
+        tensors = [self.next_obs, self.next_done, u.flat_observation, *self.out.values(), self._act_clipped,
+                   self.norm.obs_mean, self.norm.obs_var, self.norm.obs_count, self.norm.returns, self.norm.ret_mean, self.norm.ret_var, self.norm.ret_count]
+        if self.fused:
+            tensors.append(self.policy.calls)
+        return u.save_state(), [(t, t.clone()) for t in tensors]
+
+    def _restore(self, snap):
+        image, tensors = snap
+        self.env.unwrapped.load_state(image)
+        for t, saved in tensors:
+            t.copy_(saved)
+
     def _capture(self):
+        # warm-up outside the capture (lazy initialisation: function attributes, library autotuning) and the capture itself
+        # execute / record real iterations -> the state they touch is snapshotted and restored, so that the first run()
+        # starts exactly where reset() left the environments (ADVICE r1: the warm-up used to advance them by two steps)
+        snap = self._snapshot()
+        rng_state = torch.cuda.get_rng_state(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(2):  # warm-up outside the capture (lazy initialisation, autotuning)
+            for _ in range(2):
                 self._iteration()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
@@ -412,6 +433,9 @@ class PolicyRollout:
         # kernels of THIS library recorded into one graph replay: the handles count launches at capture time; the fused loop's
         # evac_normalize_reward is a handle-less entry point (+1)
         self.launches_per_iteration = count() - before + (1 if self.fused else 0)
+        self._restore(snap)
+        torch.cuda.set_rng_state(rng_state, self.device)
+        torch.cuda.synchronize(self.device)
 
     def run(self, num_steps: int):
         """Returns the storage dict ([T, E, ...]) when `store`, else None."""

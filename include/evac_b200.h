@@ -177,6 +177,16 @@ int evac_step(EvacHandle* h, const float* actions, const float* noise, float* ob
 int evac_step_host(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward,
                    uint8_t* terminated, uint8_t* truncated, uint8_t* statuses);
 
+/* Checkpoint / resume: the COMPLETE device state of a handle -- pedestrian state, agent, time, episode index (the Philox
+ * key word), running-episode accumulators, scripted-agent state, finished-episode statistics -- as one flat byte image in
+ * DEVICE memory of evac_state_bytes(h) bytes.  The image is only meaningful for a handle created with the same
+ * configuration, number of environments and library build; together with (seed, env_index_offset) it resumes a run
+ * bit-identically (the random streams are counter-based: nothing else carries state).
+ * [the reference has no checkpointing of the environment; SURVEY.md section 5] */
+int64_t evac_state_bytes(EvacHandle* h);
+int evac_save_state(EvacHandle* h, void* image, void* stream);
+int evac_load_state(EvacHandle* h, const void* image, void* stream);
+
 /* `num_steps` consecutive steps in ONE kernel launch with the state kept on chip.
  *   agent_kind EVAC_AGENT_TABLE: actions [num_steps,E,2] float32; EVAC_AGENT_RANDOM: U[-1,1)^2
  *              from the Philox stream (RandomAgent); EVAC_AGENT_ROTATING: (sin, cos)(0.05 k);

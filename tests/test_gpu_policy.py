@@ -287,3 +287,32 @@ def test_unsupported_policy_shapes_raise():
         Fused(Torch(62 * 6, 60, num_hidden=128), 60, device="cuda")
     with pytest.raises(NotImplementedError):
         Fused(Torch(62 * 6, 60, num_heads=5), 60, device="cuda")
+
+
+def test_rollout_capture_does_not_advance_the_environments():
+    """the warm-up iterations before the CUDA-graph capture used to step the real environments (episodes started
+    two transitions in, normaliser counts off by two).  They run on a snapshot now: after reset() the first run(T) must
+    record exactly T transitions from the reset state -- same as the eager (no graph) loop, bit for bit in eval mode."""
+    import evacuation_b200 as eb
+    from evacuation_b200.rollout import FusedRPOTransformerPolicy, PolicyRollout, RPOTransformerPolicy
+
+    E, n, T = 6, 60, 5
+    outs = []
+    for use_graph in (True, False):
+        env = eb.setup_env(eb.EnvConfig(number_of_pedestrians=n), eb.EnvWrappersConfig(positions="rel", statuses="ohe", type="Box"),
+                           num_envs=E, seed=4, auto_reset=True)
+        torch.manual_seed(3)
+        net = RPOTransformerPolicy(env.unwrapped.obs_dim, n).cuda()
+        pol = FusedRPOTransformerPolicy(net, n, device="cuda", seed=9).eval()
+        ro = PolicyRollout(env, pol, use_graph=use_graph, store=True)
+        ro.reset()
+        buf = ro.run(T)
+        st = env.unwrapped.get_state()
+        assert bool((st["now"] == T).all()), st["now"]
+        assert int(pol.calls) == T and abs(float(ro.norm.obs_count) - (1e-4 + T)) < 1e-9 and abs(float(ro.norm.ret_count) - (1e-4 + T)) < 1e-9
+        assert bool((buf["dones"][0] == 0).all())
+        outs.append((buf, st))
+    for k in outs[0][0]:
+        assert torch.equal(outs[0][0][k], outs[1][0][k]), k
+    for k in outs[0][1]:
+        assert torch.equal(outs[0][1][k], outs[1][1][k]), k

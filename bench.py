@@ -412,18 +412,17 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     # kernel nodes recorded into the graph (the library counts launches at capture time) = launches of ONE timed replay
     launches = sum(x.unwrapped.launch_count for x in sets) - launches0
-    # untimed warm-up replays (beyond the W steps above): graph upload, and ~30 ms of the very workload so that the timed
-    # replay runs at settled clocks / warm instruction caches (the first replays of a freshly launched process are ~5 % slower)
+    # untimed warm-up replays (beyond the W steps above): graph upload, then ~30 ms of the very workload enqueued back to back
+    # with the timed replay, so that the K timed steps run at settled clocks / warm instruction caches.  (Measured with
+    # tools/step_bench.py: the first replays after any idle gap -- even the ~1 ms of a host synchronisation -- are 5-7 % slower;
+    # a K = 20 replay lasts 0.19 ms, so without this the driver's short run would only ever see that transient.  The host
+    # runs ahead of the device while the warm-up replays execute, which also keeps host jitter out of the event pair.)
     ramp = int(min(500, max(2, np.ceil(0.03 / (K * 10e-6)))))
-    for _ in range(ramp):
-        graph_a.replay()
+    graph_a.replay()
     barrier()
     sampler.start()
-    # device head start: the GPU spins while the host submits the K-node graph launch, so that a host thread that is briefly
-    # descheduled (N ranks + samplers share the box's cores) cannot leave a gap inside the event pair (A/B on an idle
-    # host: no difference)
-    if not os.environ.get("EVAC_BENCH_NO_HEADSTART"):
-        torch.cuda._sleep(int((1e-3 + 1e-6 * K) * 1.9e9))
+    for _ in range(ramp):
+        graph_a.replay()
     e0.record()
     graph_a.replay()
     e1.record()

@@ -875,6 +875,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
     int wac_state = (a.agent_kind == AGENT_WACUUM) ? a.agent_state[e] : 0;
     int now = a.now[e];
     int episode = a.episode[e];
+    const long long overall_start = a.overall[e];
     const int now_start = now;
     int steps_total = 0;
     double acc_r = 0, acc_i = 0, acc_s = 0;
@@ -954,9 +955,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 32 ? 32 : (THREADS == 64 
           ax = action_r.x; ay = action_r.y;
         } else if (a.agent_kind == AGENT_WACUUM) {
           wacuum_act(ap.x, ap.y, wac_state, a, ax, ay);
-        } else {  // RotatingAgent [rotating_agent.py:12-16]
-          const float ph = 0.05f * (float)now;
-          ax = sinf(ph); ay = cosf(ph);
+        } else {  // RotatingAgent [rotating_agent.py:8-16]: i counts the agent's act() calls and never restarts with an episode
+          const double ph = 0.05 * (double)(overall_start + steps_total);  // float64 like the reference
+          ax = (float)sin(ph); ay = (float)cos(ph);
         }
         const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay))), a.eps_f);
         ax = __fdiv_rn(ax, nrm); ay = __fdiv_rn(ay, nrm);

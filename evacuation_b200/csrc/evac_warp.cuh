@@ -97,12 +97,13 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
   const unsigned st2 = *st_l;
   const float4 rec0 = *reinterpret_cast<const float4*>(blk);      // agent_pos, agent_dir
   const int4 rec1 = *reinterpret_cast<const int4*>(blk + 16);     // now, episode, agent_state
-  long long overall = 0;
-  double acc_r = 0, acc_i = 0, acc_s = 0;  // lane 0: the episode accumulators of env.py:168-170
+  // overall_timesteps (all lanes: the RotatingAgent's call counter) and, lane 0, the episode accumulators of env.py:168-170
+  const longlong2 rec2 = *reinterpret_cast<const longlong2*>(blk + 32);
+  long long overall = rec2.x;
+  double acc_r = __longlong_as_double(rec2.y), acc_i = 0, acc_s = 0;
   if (lane == 0) {
-    const longlong2 r2 = *reinterpret_cast<const longlong2*>(blk + 32);
     const double2 r3 = *reinterpret_cast<const double2*>(blk + 48);
-    overall = r2.x; acc_r = __longlong_as_double(r2.y); acc_i = r3.x; acc_s = r3.y;
+    acc_i = r3.x; acc_s = r3.y;
   }
   WPed q[2];
   q[0].p = make_float2(pd0.x, pd0.y); q[0].d = make_float2(pd0.z, pd0.w); q[0].st = (int)(st2 & 0xffu);
@@ -223,9 +224,9 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
         ax = 2.f * u01(r.x) - 1.f; ay = 2.f * u01(r.y) - 1.f;
       } else if (a.agent_kind == AGENT_WACUUM) {
         wacuum_act(ap.x, ap.y, wac_state, a, ax, ay);
-      } else {  // RotatingAgent [rotating_agent.py:12-16]
-        const float ph = 0.05f * (float)now;
-        ax = sinf(ph); ay = cosf(ph);
+      } else {  // RotatingAgent [rotating_agent.py:8-16]: i counts the agent's act() calls and never restarts with an episode
+        const double ph = 0.05 * (double)(overall + 1);  // float64 like the reference
+        ax = (float)sin(ph); ay = (float)cos(ph);
       }
       const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay))), a.eps_f);
       ax = __fdiv_rn(ax, nrm); ay = __fdiv_rn(ay, nrm);

@@ -81,3 +81,25 @@ def test_efficiency_curve_is_monotone_and_bounded():
     assert mean.shape == (600,) and std.shape == (600,)
     assert (np.diff(mean) >= -1e-12).all() and mean[0] >= 0 and mean[-1] <= n   # ESCAPED is absorbing
     assert (std >= 0).all()
+
+
+def test_rotating_agent_phase_survives_auto_reset():
+    """the reference's RotatingAgent counts its act() calls (rotating_agent.py:8-16) and never restarts with an
+    episode; the on-device agent therefore takes its phase from overall_timesteps, not from the in-episode step."""
+    import evacuation_b200 as eb
+
+    n, E, T, max_t = 5, 3, 20, 7
+    env = eb.setup_env(eb.EnvConfig(number_of_pedestrians=n, max_timesteps=max_t), eb.EnvWrappersConfig(positions="rel", statuses="ohe", type="Box"),
+                       num_envs=E, seed=2, auto_reset=True)
+    env.reset()
+    obs, _, _, trunc = env.rollout(T, agent="rotating", obs_every_step=True)
+    got = obs[:, :, 0, :2].cpu().numpy()  # agent row of the Box observation: absolute agent position after every step
+    pos = np.zeros(2, dtype=np.float32)
+    for t in range(1, T + 1):
+        a = np.array([np.sin(0.05 * t), np.cos(0.05 * t)], dtype=np.float32)
+        a = a / (np.sqrt(a[0] * a[0] + a[1] * a[1]) + np.float32(1e-8))
+        pos = pos + np.float32(0.01) * a
+        if t % max_t == 0:  # same-step auto-reset: the observation shows the fresh episode, the agent back at the origin
+            pos = np.zeros(2, dtype=np.float32)
+        assert np.allclose(got[t - 1], pos[None, :], atol=1e-6), (t, got[t - 1], pos)
+    assert bool(trunc.all())

@@ -378,6 +378,11 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
     // 1024 x 1000 109 -> 107 us, 2048 x 256 (0.17 per cell) 58 -> 63 us  => on from half a pedestrian per cell
     h->cell_pair_walk = 2 * h->N >= gx * gy;
     { const char* pw = getenv("EVAC_CELL_PAIR_WALK"); if (pw) h->cell_pair_walk = atoi(pw) != 0; }
+    // bit 1 (EVAC_CELL_DYNAMIC=1, A/B): the warps draw their chunks of the paired walk from a shared counter instead of taking
+    // equal static shares; results are bit-identical.  Measured on B200 (256 x 4096, 20 steps after 0 / 64 / 300 warm-up steps):
+    // 109.2 / 147.5 / 246.1 us static vs 111.7 / 146.3 / 247.3 us dynamic -- the flocked regime is bound by the total number of
+    // candidate pairs, not by the balance between the warps of a CTA, so the static shares stay.
+    { const char* dy = getenv("EVAC_CELL_DYNAMIC"); if (h->cell_pair_walk && dy && atoi(dy) == 1) h->cell_pair_walk |= 2; }
   } else if (h->threads == 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search == EVAC_SEARCH_CELLS) {
     // one-warp kernel, opt-in: vertical strips (a 1-D cell list, at most 32 strips), same edge rule.  Measured on
     // B200 (profiles/README.md): 15 % fewer instructions than the all-pairs tile but no wall-clock gain (the warp is

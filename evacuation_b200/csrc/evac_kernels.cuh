@@ -544,6 +544,7 @@ __device__ __forceinline__ void cell_list_pass(const Tile<float>& tile, const Ce
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0 && a.cells_y == 64) cs.row_pairs[64] = run;
+    if (lane == 0) cs.row_pairs[66] = 0;  // chunk counter of the dynamic walk
   }
   __syncthreads();  // list[] (aliased by res[]) is dead from here on
   // ---- 5. walk the sorted slots
@@ -555,8 +556,24 @@ __device__ __forceinline__ void cell_list_pass(const Tile<float>& tile, const Ce
     // fails the distance test and adds an exact zero, so the sums equal the one-slot walk bit for bit.
     const int reach = a.cell_reach;
     const int n_pairs = cs.row_pairs[a.cells_y];
+    // chunks of 32 slot pairs are handed to the warps either statically (warp w: chunks w, w + WARPS, ...) or, cell_pair_walk & 2,
+    // drawn from one shared counter: a walk costs as much as its cells are crowded, so in a flocked crowd equal shares of
+    // slot pairs leave most warps waiting at the barrier for the ones that drew the dense cells.  The result of a pair does
+    // not depend on who walks it (bit-identical either way).
+    const bool dynamic = (a.cell_pair_walk & 2) != 0;
+    int* const next_chunk = cs.row_pairs + 66;  // (row_pairs has 68 entries, 65 used; zeroed below the scan barrier)
+    int chunk = warp;
 #pragma unroll 1
-    for (int t = tid; t < n_pairs; t += THREADS) {
+    for (;;) {
+      if (dynamic) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(next_chunk, 1);
+        chunk = __shfl_sync(0xffffffffu, c, 0);
+      }
+      if (chunk * 32 >= n_pairs) break;
+      const int t = chunk * 32 + lane;
+      chunk += WARPS;
+      if (t >= n_pairs) continue;
       int row = 0;
       {  // largest row with row_pairs[row] <= t
         int hi_r = a.cells_y;

@@ -608,65 +608,36 @@ class EvacuationEnv:
         return stats, fin.bool(), tot
 
     # ------------------------------------------------------------------ rendering (env.py:173-324), host-side
-    _STATUS_COLORS = {1: "tab:blue", 2: "tab:green", 3: "tab:orange", 4: "tab:gray"}  # viscek, follower, exiting, escaped
-
-    def _matplotlib(self):
-        try:
-            import matplotlib
-
-            matplotlib.use("Agg")
-            import matplotlib.pyplot as plt
-            from matplotlib import animation
-        except ImportError as exc:  # not installed in the B200 image
-            raise ImportError("render / save_animation need matplotlib, which is not installed; the recorded trajectory is "
-                              "available as env.unwrapped.pedestrians.memory / agent.memory") from exc
-        return plt, animation
-
-    def _draw_frame(self, ax, positions, statuses, agent_position):
-        w, h = self.area.width, self.area.height
-        ax.clear()
-        ax.set_xlim(-1.1 * w, 1.1 * w); ax.set_ylim(-1.1 * h, 1.1 * h); ax.set_aspect("equal")
-        ax.plot([-w, w, w, -w, -w], [-h, -h, h, h, -h], color="black", linewidth=1)
-        from matplotlib.patches import Circle
-
-        ex = self.area.exit.position
-        ax.add_patch(Circle((ex[0], ex[1]), SwitchDistances.to_exit, alpha=0.15, color="tab:orange"))
-        ax.add_patch(Circle(tuple(agent_position), SwitchDistances.to_leader, alpha=0.15, color="tab:green"))
-        for code, color in self._STATUS_COLORS.items():
-            m = statuses == code
-            ax.scatter(positions[m, 0], positions[m, 1], s=12, color=color)
-        ax.scatter([agent_position[0]], [agent_position[1]], s=40, color="red", marker="*")
+    def _render_kw(self):
+        return dict(width=self.area.width, height=self.area.height, exit_position=self.area.exit.position,
+                    to_exit=SwitchDistances.to_exit, to_escape=SwitchDistances.to_escape, to_leader=SwitchDistances.to_leader)
 
     def render(self):
-        """PNG of the tracked environment's current state into `path_png` (env.py:173-240)."""
-        plt, _ = self._matplotlib()
+        """PNG of the tracked environment's current state: `<path_png>/<experiment_name>_<now>.png` (env.py:173-240).
+        Rasterised with Pillow (evacuation_b200/render.py); returns the file name."""
+        from . import render as R
+
         st = self.get_state()
         e = self.tracked_env
-        fig, ax = plt.subplots(figsize=(5, 5))
-        self._draw_frame(ax, st["positions"][e].cpu().numpy(), st["statuses"][e].cpu().numpy(), st["agent_position"][e].cpu().numpy())
-        os.makedirs(self.path_png, exist_ok=True)
-        path = os.path.join(self.path_png, f"{self.experiment_name}_ep{self.time.n_episodes}_t{int(st['now'][e])}.png")
-        fig.savefig(path)
-        plt.close(fig)
+        now = int(st["now"][e])
+        path = os.path.join(self.path_png, f"{self.experiment_name}_{now}.png")
+        R.save_png(path, st["positions"][e].cpu().numpy(), st["statuses"][e].cpu().numpy(), st["agent_position"][e].cpu().numpy(),
+                   title=f"{self.experiment_name}. Timesteps: {now}", **self._render_kw())
+        log.info("Env is rendered and png image is saved to %s", path)
         return path
 
     def save_animation(self):
-        """GIF of the recorded trajectory (`draw=True`) into `path_giff` (env.py:241-324)."""
-        plt, animation = self._matplotlib()
+        """GIF of the recorded trajectory (`draw=True`): `<path_giff>/<experiment_name>_ep-<n_episodes>.gif`, one frame per
+        step, 20 ms per frame (env.py:241-324).  Returns the file name."""
+        from . import render as R
+
         pos, sts, ag = self.pedestrians.memory["positions"], self.pedestrians.memory["statuses"], self.agent.memory["position"]
-        if not pos:
-            raise RuntimeError("no trajectory recorded: construct the env with draw=True (or set env.unwrapped.draw) before reset()")
-        fig, ax = plt.subplots(figsize=(5, 5))
-
-        def frame(t):
-            self._draw_frame(ax, pos[t], sts[t], ag[max(t - 1, 0)] if ag else np.zeros(2))
-
-        anim = animation.FuncAnimation(fig, frame, frames=len(pos), interval=20)
-        os.makedirs(self.path_giff, exist_ok=True)
-        path = os.path.join(self.path_giff, f"{self.experiment_name}_ep{self.time.n_episodes}.gif")
-        anim.save(path, writer=animation.PillowWriter(fps=25))
-        plt.close(fig)
-        self.draw, self.save_next_episode_anim = bool(self.cfg.draw), False
+        path = os.path.join(self.path_giff, f"{self.experiment_name}_ep-{self.time.n_episodes}.gif")
+        R.save_gif(path, pos, sts, ag, title=f"{self.experiment_name}\nn_episodes = {self.time.n_episodes}", **self._render_kw())
+        log.info("Env is rendered and gif animation is saved to %s", path)
+        if self.save_next_episode_anim:  # env.py:322-324
+            self.save_next_episode_anim = False
+            self.draw = False
         return path
 
 

@@ -807,7 +807,8 @@ def test_error_behaviour_matches_reference():
 
 def test_logging_and_trajectory_capture(tmp_path):
     """`draw` records the tracked environment's trajectory like Pedestrians.save / Agent.save, reset() logs
-    the finished episode with the reference's keys (env.py:115-125), rendering needs matplotlib (absent here -> ImportError)."""
+    the finished episode with the reference's keys (env.py:115-125), `save_animation` / `render` write the reference's GIF / PNG
+    files (rasterised with Pillow, evacuation_b200/render.py)."""
     import evacuation_b200 as eb
 
     n = 10
@@ -834,12 +835,12 @@ def test_logging_and_trajectory_capture(tmp_path):
     assert list(d) == list(eb._native.EPISODE_STAT_KEYS)
     assert d["episode_length"] == 6 and d["overall_timesteps"] == 6 and abs(d["episode_reward"] - total) <= 1e-4 * abs(total)
     assert d["escaped_pedestrians"] + d["exiting_pedestrians"] + d["following_pedestrians"] + d["viscek_pedestrians"] == n
-    try:
-        import matplotlib  # noqa: F401
-        assert os.path.exists(u.save_animation())
-    except ImportError:
-        with pytest.raises(ImportError):
-            u.save_animation()
+    from PIL import Image
+
+    gif = u.save_animation()   # env.py:241-324, file name like the reference's: <experiment_name>_ep-<n_episodes>.gif
+    assert gif.endswith(os.path.join("giff", "t_ep-1.gif")) and Image.open(gif).n_frames == 6
+    png = u.render()           # env.py:173-240: <experiment_name>_<now>.png
+    assert png.endswith(os.path.join("png", "t_6.png")) and Image.open(png).size == (500, 500)
     env.reset()  # logs the finished episode like env.py:114-127
     assert u.last_episode_log["episode_length"] == 6 and u.time.n_episodes == 2
     logfile = tmp_path / "logs" / "logs_t.log"

@@ -337,3 +337,40 @@ def test_bind_host_to_device_never_raises():
     assert after and after <= before
     if not info["bound"]:
         assert after == before and "reason" in info
+
+
+def test_renderer_draws_the_reference_scene(tmp_path):
+    """`render` / `save_animation` (env.py:173-324) rasterised with Pillow (matplotlib is absent from the
+    image, so round 1's matplotlib code had never executed).  The scene is checked pixel-wise: pedestrians carry the
+    status colours of matplotlib's default cycle in Status.all() order, the exiting zone is a green half disc ABOVE the exit,
+    the following zone surrounds the agent, the GIF holds one 20 ms frame per recorded step."""
+    from PIL import Image
+
+    from evacuation_b200 import render as R
+
+    pos = np.array([[0.5, 0.5], [-0.5, 0.5], [0.0, -0.8], [0.0, -1.0], [-0.7, -0.6]])
+    st = np.array([1, 2, 3, 4, 1], dtype=np.uint8)
+    img = R.draw_frame(pos, st, (0.3, 0.2), title="exp. Timesteps: 7")
+    assert img.size == (R.SIZE, R.SIZE) and img.mode == "RGB"
+    view = R._View(1.0, 1.0)
+
+    def at(x, y):
+        px, py = view.px(x, y)
+        return img.getpixel((int(round(float(px))), int(round(float(py)))))
+
+    assert at(0.5, 0.5) == R.STATUS_COLORS[1] and at(-0.5, 0.5) == R.STATUS_COLORS[2] and at(0.0, -0.8) == R.STATUS_COLORS[3]
+    g = at(0.25, -0.9)           # inside the exiting zone (radius 0.4 around (0, -1), upper half): white blended with green at 0.2
+    assert g[1] > g[0] and g[1] > g[2] and g != (255, 255, 255)
+    assert at(0.25, -1.08) == (255, 255, 255)    # below the exit: outside the half disc
+    b = at(0.3, 0.32)            # inside the following zone (radius 0.2 around the agent): white blended with blue at 0.1
+    assert b[2] > b[0] and b[2] == 255 and b[0] < 255
+    assert at(0.9, 0.9) == (255, 255, 255)
+    png = R.save_png(str(tmp_path / "png" / "exp_7.png"), pos, st, (0.3, 0.2))
+    assert Image.open(png).size == (R.SIZE, R.SIZE)
+    T_ = 6
+    traj = [pos + 0.01 * t for t in range(T_ + 1)]
+    gif = R.save_gif(str(tmp_path / "giff" / "exp_ep-1.gif"), traj, [st] * (T_ + 1), [np.array([0.01 * t, 0.0]) for t in range(T_)], title="exp\nn_episodes = 1")
+    im = Image.open(gif)
+    assert im.n_frames == T_ and im.info.get("duration") == 20
+    with pytest.raises(RuntimeError):
+        R.save_gif(str(tmp_path / "x.gif"), [], [], [])

@@ -383,6 +383,12 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
     // 109.2 / 147.5 / 246.1 us static vs 111.7 / 146.3 / 247.3 us dynamic -- the flocked regime is bound by the total number of
     // candidate pairs, not by the balance between the warps of a CTA, so the static shares stay.
     { const char* dy = getenv("EVAC_CELL_DYNAMIC"); if (h->cell_pair_walk && dy && atoi(dy) == 1) h->cell_pair_walk |= 2; }
+    // bit 2 (EVAC_CELL_GROUP=1, A/B): grouped walk -- four lanes share one window of 8 consecutive sorted slots, a quarter of the
+    // shared-memory wavefronts for ~25 % more candidates; one-CTA kernels only; bit-identical results.  Measured on B200
+    // (256 x 4096, 20 steps after 0 / 64 / 300 warm-up steps): 109.8 / 147.8 / 246.1 us paired vs 118.1 / 153.4 / 247.9 us grouped
+    // (128 x 8192: 226.9 vs 234.6; 1024 x 1000: 85.1 vs 89.9) -- the walk is not bound by shared-memory bandwidth either: what it
+    // costs is the number of evaluated candidate pairs times the trip-count divergence inside a warp, so the paired walk stays.
+    { const char* gr = getenv("EVAC_CELL_GROUP"); if (h->cell_pair_walk && h->cluster == 1 && gr && atoi(gr) == 1) h->cell_pair_walk |= 4; }
   } else if (h->threads == 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search == EVAC_SEARCH_CELLS) {
     // one-warp kernel, opt-in: vertical strips (a 1-D cell list, at most 32 strips), same edge rule.  Measured on
     // B200 (profiles/README.md): 15 % fewer instructions than the all-pairs tile but no wall-clock gain (the warp is
@@ -902,7 +908,11 @@ int evac_probe_pairwise(int32_t device, int32_t num_envs, int32_t n, int32_t rep
   const size_t tb = Tile<float>::bytes(64);
   for (int rep = 0; rep < 2; ++rep) {
     CK(cudaEventRecord(e0));
-    if (shape_32x2 && wpc == 2) probe_pairwise_kernel<32, 2, 4, 2, 20><<<(num_envs + 1) / 2, 64, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    const char* hw = getenv("EVAC_PROBE_HALFWARP");  // A/B: 16 lanes x 4 pedestrians per environment, two environments per warp (unroll 1 | 2 | 4)
+    if (hw && atoi(hw) == 1) probe_pairwise_kernel<16, 4, 1, 2, 16><<<(num_envs + 1) / 2, 32, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    else if (hw && atoi(hw) == 2) probe_pairwise_kernel<16, 4, 2, 2, 16><<<(num_envs + 1) / 2, 32, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    else if (hw && atoi(hw) == 4) probe_pairwise_kernel<16, 4, 4, 2, 16><<<(num_envs + 1) / 2, 32, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    else if (shape_32x2 && wpc == 2) probe_pairwise_kernel<32, 2, 4, 2, 20><<<(num_envs + 1) / 2, 64, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
     else if (shape_32x2 && wpc == 4) probe_pairwise_kernel<32, 2, 4, 4, 10><<<(num_envs + 3) / 4, 128, 4 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
     else if (shape_32x2 && unr == 8) probe_pairwise_kernel<32, 2, 8><<<num_envs, 32, tb>>>(pos, unit, out, n, reps, thr2, num_envs);
     else if (shape_32x2 && unr == 2) probe_pairwise_kernel<32, 2, 2><<<num_envs, 32, tb>>>(pos, unit, out, n, reps, thr2, num_envs);

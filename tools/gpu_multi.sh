@@ -1,5 +1,5 @@
 #!/bin/bash
-# 2-GPU contract run under torchrun (C2 weak scaling + C5 strong scaling in the same line) + the reference arm launched the same way
+# N-GPU contract run under torchrun (usage: bash tools/gpu_multi.sh <tag> <N>; gpurun --gpus N) (C2 weak scaling + C5 strong scaling in the same line) + the reference arm launched the same way
 TAG=${1:-r02i}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT

@@ -63,8 +63,8 @@ template <int MODE, int WPC>
 __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kernel(const __grid_constant__ KArgs<float> a) {  // @region wload
   // Tile<float> of 64 slots (+ the look-ahead entries) per warp = 66 float4.  EVAC_OBS_STAGED (A/B variant): after the pairwise
   // pass the same memory stages the observation row ((64 + 2) x 6 floats = 99 float4), see the observation section
-#ifdef EVAC_OBS_STAGED
-  __shared__ __align__(16) float4 tile_all[WPC][99];
+#if defined(EVAC_OBS_STAGED) || defined(EVAC_OBS_BULK)
+  __shared__ __align__(128) float4 tile_all[WPC][99];
 #else
   __shared__ __align__(16) float4 tile_all[WPC][66];
 #endif
@@ -354,9 +354,11 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
         // lane and round -- 512 contiguous bytes per warp instruction.  Measured on B200, same box, 4096 x 60 per-step regime:
         // the load -> observe -> write-back skeleton gets faster (5.23 -> 4.82 us) but the FULL step slower (8.42 -> 8.66 us:
         // STS -> LDS -> STG adds a dependent shared-memory round trip to every warp's tail), so the direct stores stay.
+        // EVAC_OBS_BULK: the staged row leaves as ONE cp.async.bulk (shared -> global, the TMA engine's 1-D path; UBLKCP in the
+        // SASS) issued by lane 0, its wait deferred behind the state write-back: 8.76 vs 8.52 us, same box -- also slower.
         const float inv_hyp = (float)(1.0 / 1.41421353816986083984375);
         const float2 nap = make_float2(-ap.x, -ap.y);
-#ifndef EVAC_OBS_STAGED
+#if !defined(EVAC_OBS_STAGED) && !defined(EVAC_OBS_BULK)
         if (lane == 0) {
           const float2 ex = __fmul2_rn(__fadd2_rn(exit_p, nap), splat(inv_hyp));
           float2* r = reinterpret_cast<float2*>(row);
@@ -390,6 +392,28 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
             r[2] = make_float2(st == ST_FOLLOWER ? 1.f : 0.f, st == ST_VISCEK ? 1.f : 0.f);
           }
         }
+#ifdef EVAC_OBS_BULK
+        // A/B variant: the staged row leaves the SM as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the TMA
+        // engine's 1-D path) issued by lane 0, N even (24 (N + 2) bytes is then a multiple of 16)
+        if ((N & 1) == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile_all[wic]);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(row), "r"(src), "r"((N + 2) * 24) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the tile may only be rewritten (next step) once the copy has read it; after the last step the wait moves behind
+            // the state write-back at the end of the kernel
+            if (s != a.num_steps - 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+        } else {
+          __syncwarp();
+          const int n8 = (N + 2) * 3;
+          float2* dst = reinterpret_cast<float2*>(row);
+#pragma unroll
+          for (int c = 0; c < 7; ++c) { const int j = lane + 32 * c; if (j < n8) dst[j] = stage[j]; }
+        }
+#else
         __syncwarp();
         if ((N & 1) == 0) {
           const int n16 = (N + 2) * 3 / 2;  // float4 chunks of the row
@@ -403,6 +427,7 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
 #pragma unroll
           for (int c = 0; c < 7; ++c) { const int j = lane + 32 * c; if (j < n8) dst[j] = stage[j]; }
         }
+#endif
 #endif
       } else if (MODE == WMODE_GRAV || a.positions == POS_GRAV) {
         float gx = 0.f, gy = 0.f;
@@ -447,6 +472,9 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
     if (a.reward) a.reward[e] = reward_sum;
     if (a.terminated) a.terminated[e] = (uint8_t)any_term;
     if (a.truncated) a.truncated[e] = (uint8_t)any_trunc;
+#ifdef EVAC_OBS_BULK
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
   }
 }
 

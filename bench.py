@@ -688,6 +688,20 @@ def pairwise_probe(device_index):
                                          "ordered_pairs_per_s": best}
     head = out["cases"][f"{ENVS_PER_GPU}x{N_PED}"]
     out["achieved"], out["frac"] = head["achieved"], head["frac"]
+    # beside it, NOT the fused kernel's shape: 16 lanes x 4 pedestrians per environment, two environments per warp (fewer LDS
+    # and loop instructions per evaluated pair; needs many warps: better at 65 536 envs, worse at 4096)
+    os.environ["EVAC_PROBE_HALFWARP"] = "2"
+    try:
+        var = {}
+        for E, reps in ((ENVS_PER_GPU, 200), (65536, 50)):
+            best = 0.0
+            for _ in range(3):
+                nat.check(lib.evac_probe_pairwise(device_index, E, N_PED, reps, C.byref(ms), C.byref(pairs)))
+                best = max(best, pairs.value / (ms.value * 1e-3))
+            var[f"{E}x{N_PED}"] = {"achieved": best * 8 / 1e12, "frac": best * 8 / 1e12 / peak}
+        out["variant_16x4_two_envs_per_warp"] = var
+    finally:
+        os.environ.pop("EVAC_PROBE_HALFWARP", None)
     return out
 
 

@@ -430,11 +430,29 @@ __global__ void __launch_bounds__(32 * WPC, EVAC_WARP_MINB / WPC) evac_warp_kern
 #endif
 #endif
       } else if (MODE == WMODE_GRAV || a.positions == POS_GRAV) {
+        // gravity encoding [gravity_encoding.py:8-38]: per VISCEK pedestrian -alpha / (|R| + eps)^(alpha + 2) * R, R = agent - p.
+        // Straight-line and unconditional for both pedestrians of the lane (select, not branch); MUFU square root and
+        // reciprocal (~2 ulp each against the parity bar of 2e-5 of the largest term); the two sums over the warp in double.
         float gx = 0.f, gy = 0.f;
         int nf = 0;
+        const float alpha = (float)a.alpha, eps = (float)a.eps;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          if (q[k].st == ST_VISCEK) { float tx, ty; grav_term<float>(q[k].p.x, q[k].p.y, ap.x, ap.y, a, tx, ty); gx += tx; gy += ty; }
+          const float2 R = __fadd2_rn(ap, make_float2(-q[k].p.x, -q[k].p.y));
+          const float norm = sqrt_fast(fmaf(R.x, R.x, R.y * R.y)) + eps;
+          const float n2 = norm * norm;
+          float pw;
+          switch (a.alpha_plus2_int) {  // alpha = 2 .. 5 (BASELINE config 3) without a loop
+            case 4: pw = n2 * n2; break;
+            case 5: pw = n2 * n2 * norm; break;
+            case 6: pw = n2 * n2 * n2; break;
+            case 7: pw = n2 * n2 * n2 * norm; break;
+            default: pw = a.alpha_plus2_int ? ipow(norm, a.alpha_plus2_int) : powf(norm, alpha + 2.f);
+          }
+          const float c = __fdividef(-alpha, pw);
+          const bool vk = q[k].st == ST_VISCEK;
+          gx += vk ? c * R.x : 0.f;
+          gy += vk ? c * R.y : 0.f;
           nf += (q[k].st == ST_FOLLOWER);
         }
         nf = __reduce_add_sync(0xffffffffu, nf);

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -11,6 +12,7 @@
 
 #include "../../include/evac_b200.h"
 #include "evac_policy.cuh"
+#include "evac_policy_tc.cuh"
 
 using namespace evacp;
 
@@ -40,6 +42,10 @@ struct EvacPolicy {
   float *d_w1t = nullptr, *d_b1 = nullptr, *d_w2t = nullptr, *d_b2 = nullptr, *d_w3 = nullptr, *d_b3 = nullptr, *d_logstd = nullptr;
   float* d_scratch = nullptr;  // embedding scratch [scratch_envs, K]
   int scratch_envs = 0;
+  // layer 1 of the heads on the tensor cores (evac_policy_tc.cuh): split + swizzled weight tiles for both column tilings, H1 scratch
+  float *d_w1tc64 = nullptr, *d_w1tc128 = nullptr, *d_h1 = nullptr;
+  int h1_envs = 0, tc_chunks = 0;
+  bool use_tc = false;
   bool loaded = false;
   int64_t launches = 0;
   size_t embed_smem = 0, heads_smem = 0;
@@ -111,6 +117,15 @@ static int launch_embed(EvacPolicy* p, const PArgs& a, bool train, cudaStream_t 
   return EVAC_OK;
 }
 
+// H1 scratch [max_envs, 128] between the tensor-core layer 1 and the rest of the heads
+static int reserve_h1(EvacPolicy* p, int max_envs) {
+  if (!p->use_tc || max_envs <= p->h1_envs) return EVAC_OK;
+  if (p->d_h1) { PCK(cudaDeviceSynchronize()); PCK(cudaFree(p->d_h1)); p->d_h1 = nullptr; p->h1_envs = 0; }
+  PCK(cudaMalloc(&p->d_h1, (size_t)max_envs * TC_COLS * sizeof(float)));
+  p->h1_envs = max_envs;
+  return EVAC_OK;
+}
+
 extern "C" {
 
 int evac_policy_default_config(EvacPolicyConfig* cfg, int32_t number_of_pedestrians, int32_t d_model) {
@@ -161,6 +176,14 @@ int evac_policy_create(const EvacPolicyConfig* cfg, int32_t device, EvacPolicy**
   alloc(&p->d_w1t, (size_t)p->K16 * HD_COLS); alloc(&p->d_b1, HD_COLS);
   alloc(&p->d_w2t, (size_t)HD_HS * HD_COLS); alloc(&p->d_b2, HD_COLS);
   alloc(&p->d_w3, (size_t)(1 + p->A) * HD_HS); alloc(&p->d_b3, 4); alloc(&p->d_logstd, 4);
+  // EVAC_POLICY_TC=0 keeps layer 1 of the heads on the CUDA cores (A/B switch); the tensor-core kernel reads float4 rows (K % 4 == 0)
+  const char* tc_env = getenv("EVAC_POLICY_TC");
+  p->use_tc = (p->K % 4 == 0) && !(tc_env && tc_env[0] == '0');
+  p->tc_chunks = (p->K + TC_KC - 1) / TC_KC;
+  if (p->use_tc) {
+    alloc(&p->d_w1tc64, (size_t)p->tc_chunks * 2 * TC_COLS * TC_KC);
+    alloc(&p->d_w1tc128, (size_t)p->tc_chunks * 2 * TC_COLS * TC_KC);
+  }
   if (e != cudaSuccess) { evac_policy_destroy(p); return pfail(EVAC_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
   *out = p;
   return EVAC_OK;
@@ -169,7 +192,7 @@ int evac_policy_create(const EvacPolicyConfig* cfg, int32_t device, EvacPolicy**
 int evac_policy_destroy(EvacPolicy* p) {
   if (!p) return EVAC_OK;
   cudaSetDevice(p->device);
-  float* bufs[] = {p->d_emb_w, p->d_w1t, p->d_b1, p->d_w2t, p->d_b2, p->d_w3, p->d_b3, p->d_logstd, p->d_scratch};
+  float* bufs[] = {p->d_emb_w, p->d_w1t, p->d_b1, p->d_w2t, p->d_b2, p->d_w3, p->d_b3, p->d_logstd, p->d_scratch, p->d_w1tc64, p->d_w1tc128, p->d_h1};
   for (float* b : bufs) if (b) cudaFree(b);
   delete p;
   return EVAC_OK;
@@ -224,14 +247,37 @@ int evac_policy_load_weights(EvacPolicy* p, const float* w, int64_t count) {
   PCK(cudaMemcpy(p->d_w3, w3.data(), w3.size() * sizeof(float), cudaMemcpyHostToDevice));
   PCK(cudaMemcpy(p->d_b3, b3.data(), b3.size() * sizeof(float), cudaMemcpyHostToDevice));
   PCK(cudaMemcpy(p->d_logstd, ls.data(), ls.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (p->use_tc) {
+    // per 32-k chunk and column tile: [hi tile | lo tile], NT rows (columns of W1) x 32 k, K-major SWIZZLE_128B (tc_swizzle)
+    for (int NT : {64, 128}) {
+      const int ny = TC_COLS / NT;
+      std::vector<float> t((size_t)p->tc_chunks * 2 * TC_COLS * TC_KC, 0.f);
+      for (int c = 0; c < p->tc_chunks; ++c)
+        for (int y = 0; y < ny; ++y) {
+          float* hi = t.data() + ((size_t)c * ny + y) * (2 * NT * TC_KC);
+          float* lo = hi + NT * TC_KC;
+          for (int n = 0; n < NT; ++n)
+            for (int kk = 0; kk < TC_KC; ++kk) {
+              const int k = c * TC_KC + kk;
+              const float v = k < K ? w1t[(size_t)k * HD_COLS + y * NT + n] : 0.f;
+              const float h = tc_hi(v);
+              const size_t off = tc_swizzle(n, kk >> 2) / 4 + (kk & 3);
+              hi[off] = h; lo[off] = v - h;
+            }
+        }
+      PCK(cudaMemcpy(NT == 64 ? p->d_w1tc64 : p->d_w1tc128, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+  }
   p->loaded = true;
   return EVAC_OK;
 }
 
 int evac_policy_reserve(EvacPolicy* p, int32_t max_envs) {
   if (!p || max_envs < 1) return pfail(EVAC_ERR_INVALID, "bad arguments");
-  if (max_envs <= p->scratch_envs) return EVAC_OK;
   PCK(cudaSetDevice(p->device));
+  const int rc = reserve_h1(p, max_envs);
+  if (rc) return rc;
+  if (max_envs <= p->scratch_envs) return EVAC_OK;
   if (p->d_scratch) { PCK(cudaDeviceSynchronize()); PCK(cudaFree(p->d_scratch)); p->d_scratch = nullptr; p->scratch_envs = 0; }
   PCK(cudaMalloc(&p->d_scratch, (size_t)max_envs * p->K * sizeof(float)));
   p->scratch_envs = max_envs;
@@ -248,16 +294,15 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
   PCK(cudaSetDevice(p->device));
   const bool heads = io->mean || io->value || io->action || io->action_clipped || io->logprob || io->entropy;
   float* emb = io->embedding;
-  if (!emb) {
-    if (p->scratch_envs < io->num_envs) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      PCK(cudaStreamIsCapturing(st, &cs));
-      if (cs != cudaStreamCaptureStatusNone) return pfail(EVAC_ERR_INVALID, "call evac_policy_reserve(%d) before capturing a forward without an embedding buffer", io->num_envs);
-      const int rc = evac_policy_reserve(p, io->num_envs);
-      if (rc) return rc;
-    }
-    emb = p->d_scratch;
+  const bool need_scratch = !emb && p->scratch_envs < io->num_envs, need_h1 = heads && p->use_tc && p->h1_envs < io->num_envs;
+  if (need_scratch || need_h1) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    PCK(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone) return pfail(EVAC_ERR_INVALID, "call evac_policy_reserve(%d) before capturing a forward", io->num_envs);
+    const int rc = need_scratch ? evac_policy_reserve(p, io->num_envs) : reserve_h1(p, io->num_envs);
+    if (rc) return rc;
   }
+  if (!emb) emb = p->d_scratch;
   const bool train = io->training != 0 && p->cfg.dropout > 0.f;
   PArgs a;
   memset(&a, 0, sizeof(a));
@@ -287,6 +332,23 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
   h.mean = io->mean; h.value = io->value; h.action = io->action; h.action_clipped = io->action_clipped; h.logprob = io->logprob; h.entropy = io->entropy;
   h.sample = io->sample;
   h.seed_lo = a.seed_lo; h.seed_hi = a.seed_hi; h.offset = a.offset; h.offset_dev = a.offset_dev; h.env_offset = io->env_index_offset;
+  if (p->use_tc) {
+    // layer 1 on the tensor cores; 64-column tiles (two CTAs per 128 environments) while 128-column tiles would not fill the SMs
+    TCArgs t;
+    t.E = h.E; t.K = p->K; t.chunks = p->tc_chunks; t.emb = emb; t.b1 = p->d_b1; t.h1 = p->d_h1;
+    const int gx = (h.E + TC_M - 1) / TC_M;
+    static thread_local bool tc_attr[16] = {false};
+    if (!tc_attr[p->device & 15]) {
+      PCK(cudaFuncSetAttribute(evac_policy_l1_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCShape<64>::SMEM_BYTES));
+      PCK(cudaFuncSetAttribute(evac_policy_l1_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCShape<128>::SMEM_BYTES));
+      tc_attr[p->device & 15] = true;
+    }
+    if (gx < 2 * 148) { t.w1tc = p->d_w1tc64; evac_policy_l1_tc_kernel<64><<<dim3(gx, 2), TC_THREADS, TCShape<64>::SMEM_BYTES, st>>>(t); }
+    else { t.w1tc = p->d_w1tc128; evac_policy_l1_tc_kernel<128><<<dim3(gx, 1), TC_THREADS, TCShape<128>::SMEM_BYTES, st>>>(t); }
+    PCK(cudaGetLastError());
+    p->launches++;
+    h.h1_in = p->d_h1;
+  }
   static thread_local size_t hattr[16] = {0};
   if (p->heads_smem > 48 * 1024 && hattr[p->device & 15] < p->heads_smem) {
     PCK(cudaFuncSetAttribute(evac_policy_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->heads_smem));

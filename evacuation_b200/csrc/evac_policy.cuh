@@ -433,6 +433,7 @@ constexpr size_t HD_SMEM_FLOATS = HD_STAGES * HD_KC * HD_COLS + HD_STAGES * HD_T
 struct HArgs {
   int E, K, K16, NH, A;          // K = S * D inputs, K16 = K rounded up to the chunk
   const float* emb;              // [E, K]
+  const float* h1_in;            // optional [E, 128]: tanh(layer 1) already computed (evac_policy_l1_tc_kernel) -> layer 1 is skipped here
   const float* w1t;              // [K16, 128]  column o < 64: critic.0.weight[o], 64 <= o: actor_mean.0.weight[o - 64] (zero padded)
   const float* b1;               // [128]
   const float* w2t;              // [64, 128]   row k, column o: (critic|actor).2.weight[o % 64][k] of o's own head (zero padded)
@@ -545,7 +546,15 @@ __global__ void __launch_bounds__(HD_THREADS, 2) evac_policy_heads_kernel(const 
 
   float acc[8][8];
   // ---- layer 1
-  {
+  if (a.h1_in != nullptr) {   // computed on the tensor cores: stage the CTA's rows of H1 next to the layer-2 weights
+    for (int v = tid; v < HD_HS * HD_COLS / 4; v += HD_THREADS) cp_async16(w2s + 4 * v, a.w2t + 4 * v, 16);
+    for (int v = tid; v < HD_TM * HD_COLS / 4; v += HD_THREADS) {
+      const int r = v / (HD_COLS / 4), q = v - r * (HD_COLS / 4);
+      cp_async16(h1 + r * HD_H1S + 4 * q, a.h1_in + (size_t)(e0 + min(r, ne - 1)) * HD_COLS + 4 * q, 16);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  } else {
     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
     if (kg == 0) { ba = *reinterpret_cast<const float4*>(a.b1 + 4 * cq); bb = *reinterpret_cast<const float4*>(a.b1 + HD_HS + 4 * cq); }
 #pragma unroll

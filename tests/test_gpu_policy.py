@@ -115,6 +115,44 @@ def test_fused_policy_shapes_vs_torch(n_ped, d_model, kw):
     _check(net, fused, x, atol=4e-5 if kw.get("use_resid") else 2e-5)
 
 
+@pytest.mark.parametrize("E", [5, 129, 4096, 38000])
+def test_heads_on_tensor_cores_match_the_cuda_core_path_and_float64(E, monkeypatch):
+    """Layer 1 of the heads ([E x 372] x [372 x 128]) runs as 3xTF32 tcgen05 MMAs (csrc/evac_policy_tc.cuh; 64-column tiles
+    below 296 row tiles, 128-column tiles above: E = 38000).  EVAC_POLICY_TC=0 (read at evac_policy_create) keeps it on the
+    CUDA cores.  Both must sit within float32 rounding of a float64 evaluation of the heads on the kernel's own embedding
+    [rpo_linear_agent_network.py:23-42]."""
+    Fused, _, Torch, _, _ = _mods()
+    torch.manual_seed(11)
+    net = Torch(372, 60).cuda().eval()
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith("bias"):
+                p.add_(0.3 * torch.randn_like(p))
+    x = (torch.randn(E, 372, device="cuda") * 0.7).clamp_(-1, 1)
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("EVAC_POLICY_TC", tc)
+        fused = Fused(net, 60, device="cuda", seed=7).eval()
+        emb = torch.empty_like(x)
+        mean, val, lp = torch.empty((E, 2), device="cuda"), torch.empty(E, device="cuda"), torch.empty(E, device="cuda")
+        act = torch.empty((E, 2), device="cuda")
+        fused.forward(x, embedding=emb, mean=mean, value=val, action=act, logprob=lp, sample=True)
+        torch.cuda.synchronize()
+        outs[tc] = (emb, mean, val, act, lp)
+    assert torch.equal(outs["1"][0], outs["0"][0])
+    net64 = Torch(372, 60).double().cuda().eval()
+    net64.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    with torch.no_grad():
+        e64 = outs["1"][0].double()
+        mean64, val64 = net64.actor_mean(e64), net64.critic(e64).flatten()
+    for tc in ("1", "0"):
+        assert float((outs[tc][1].double() - mean64).abs().max()) < 2e-6, tc
+        assert float((outs[tc][2].double() - val64).abs().max() / val64.abs().max().clamp_min(1.0)) < 4e-6, tc
+    # the sampled action is mean + std * noise with noise keyed by (seed, call, env): identical streams on both paths
+    np.testing.assert_allclose(outs["1"][3].cpu().numpy(), outs["0"][3].cpu().numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(outs["1"][4].cpu().numpy(), outs["0"][4].cpu().numpy(), rtol=0, atol=2e-5)
+
+
 def test_fused_policy_large_logits_take_the_exact_softmax_path():
     """Attention logits of magnitude ~1e2-1e3: the Cauchy-Schwarz shift underflows whole rows, which must be redone
     with the exact maximum (near one-hot softmax); compared with a float64 evaluation of the torch restatement."""

@@ -43,8 +43,8 @@ struct EvacPolicy {
   float* d_scratch = nullptr;  // embedding scratch [scratch_envs, K]
   int scratch_envs = 0;
   // layer 1 of the heads on the tensor cores (evac_policy_tc.cuh): split + swizzled weight tiles for both column tilings, H1 scratch
-  float *d_w1tc64 = nullptr, *d_w1tc128 = nullptr, *d_h1 = nullptr;
-  int h1_envs = 0, tc_chunks = 0;
+  float *d_w1tc64 = nullptr, *d_w1tc128 = nullptr, *d_w2tc = nullptr;
+  int tc_chunks = 0;
   bool use_tc = false;
   bool loaded = false;
   int64_t launches = 0;
@@ -117,15 +117,6 @@ static int launch_embed(EvacPolicy* p, const PArgs& a, bool train, cudaStream_t 
   return EVAC_OK;
 }
 
-// H1 scratch [max_envs, 128] between the tensor-core layer 1 and the rest of the heads
-static int reserve_h1(EvacPolicy* p, int max_envs) {
-  if (!p->use_tc || max_envs <= p->h1_envs) return EVAC_OK;
-  if (p->d_h1) { PCK(cudaDeviceSynchronize()); PCK(cudaFree(p->d_h1)); p->d_h1 = nullptr; p->h1_envs = 0; }
-  PCK(cudaMalloc(&p->d_h1, (size_t)max_envs * TC_COLS * sizeof(float)));
-  p->h1_envs = max_envs;
-  return EVAC_OK;
-}
-
 extern "C" {
 
 int evac_policy_default_config(EvacPolicyConfig* cfg, int32_t number_of_pedestrians, int32_t d_model) {
@@ -183,6 +174,7 @@ int evac_policy_create(const EvacPolicyConfig* cfg, int32_t device, EvacPolicy**
   if (p->use_tc) {
     alloc(&p->d_w1tc64, (size_t)p->tc_chunks * 2 * TC_COLS * TC_KC);
     alloc(&p->d_w1tc128, (size_t)p->tc_chunks * 2 * TC_COLS * TC_KC);
+    alloc(&p->d_w2tc, (size_t)2 * TC_W2_HEAD_BYTES / 4);
   }
   if (e != cudaSuccess) { evac_policy_destroy(p); return pfail(EVAC_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
   *out = p;
@@ -192,7 +184,7 @@ int evac_policy_create(const EvacPolicyConfig* cfg, int32_t device, EvacPolicy**
 int evac_policy_destroy(EvacPolicy* p) {
   if (!p) return EVAC_OK;
   cudaSetDevice(p->device);
-  float* bufs[] = {p->d_emb_w, p->d_w1t, p->d_b1, p->d_w2t, p->d_b2, p->d_w3, p->d_b3, p->d_logstd, p->d_scratch, p->d_w1tc64, p->d_w1tc128, p->d_h1};
+  float* bufs[] = {p->d_emb_w, p->d_w1t, p->d_b1, p->d_w2t, p->d_b2, p->d_w3, p->d_b3, p->d_logstd, p->d_scratch, p->d_w1tc64, p->d_w1tc128, p->d_w2tc};
   for (float* b : bufs) if (b) cudaFree(b);
   delete p;
   return EVAC_OK;
@@ -268,16 +260,31 @@ int evac_policy_load_weights(EvacPolicy* p, const float* w, int64_t count) {
       PCK(cudaMemcpy(NT == 64 ? p->d_w1tc64 : p->d_w1tc128, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
   }
+  if (p->use_tc) {
+    // layer 2, per head: [k-chunk (2)][hi tile | lo tile], 64 rows (output columns of the head) x 32 k
+    std::vector<float> t((size_t)2 * TC_W2_HEAD_BYTES / 4, 0.f);
+    for (int hd = 0; hd < 2; ++hd)
+      for (int c = 0; c < HD_HS / TC_KC; ++c) {
+        float* hi = t.data() + (size_t)hd * (TC_W2_HEAD_BYTES / 4) + (size_t)c * (2 * HD_HS * TC_KC);
+        float* lo = hi + HD_HS * TC_KC;
+        for (int n = 0; n < HD_HS; ++n)
+          for (int kk = 0; kk < TC_KC; ++kk) {
+            const float v = w2t[(size_t)(c * TC_KC + kk) * HD_COLS + hd * HD_HS + n];
+            const float hv = tc_hi(v);
+            const size_t off = tc_swizzle(n, kk >> 2) / 4 + (kk & 3);
+            hi[off] = hv; lo[off] = v - hv;
+          }
+      }
+    PCK(cudaMemcpy(p->d_w2tc, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   p->loaded = true;
   return EVAC_OK;
 }
 
 int evac_policy_reserve(EvacPolicy* p, int32_t max_envs) {
   if (!p || max_envs < 1) return pfail(EVAC_ERR_INVALID, "bad arguments");
-  PCK(cudaSetDevice(p->device));
-  const int rc = reserve_h1(p, max_envs);
-  if (rc) return rc;
   if (max_envs <= p->scratch_envs) return EVAC_OK;
+  PCK(cudaSetDevice(p->device));
   if (p->d_scratch) { PCK(cudaDeviceSynchronize()); PCK(cudaFree(p->d_scratch)); p->d_scratch = nullptr; p->scratch_envs = 0; }
   PCK(cudaMalloc(&p->d_scratch, (size_t)max_envs * p->K * sizeof(float)));
   p->scratch_envs = max_envs;
@@ -294,12 +301,11 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
   PCK(cudaSetDevice(p->device));
   const bool heads = io->mean || io->value || io->action || io->action_clipped || io->logprob || io->entropy;
   float* emb = io->embedding;
-  const bool need_scratch = !emb && p->scratch_envs < io->num_envs, need_h1 = heads && p->use_tc && p->h1_envs < io->num_envs;
-  if (need_scratch || need_h1) {
+  if (!emb && p->scratch_envs < io->num_envs) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     PCK(cudaStreamIsCapturing(st, &cs));
-    if (cs != cudaStreamCaptureStatusNone) return pfail(EVAC_ERR_INVALID, "call evac_policy_reserve(%d) before capturing a forward", io->num_envs);
-    const int rc = need_scratch ? evac_policy_reserve(p, io->num_envs) : reserve_h1(p, io->num_envs);
+    if (cs != cudaStreamCaptureStatusNone) return pfail(EVAC_ERR_INVALID, "call evac_policy_reserve(%d) before capturing a forward without an embedding buffer", io->num_envs);
+    const int rc = evac_policy_reserve(p, io->num_envs);
     if (rc) return rc;
   }
   if (!emb) emb = p->d_scratch;
@@ -333,21 +339,21 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
   h.sample = io->sample;
   h.seed_lo = a.seed_lo; h.seed_hi = a.seed_hi; h.offset = a.offset; h.offset_dev = a.offset_dev; h.env_offset = io->env_index_offset;
   if (p->use_tc) {
-    // layer 1 on the tensor cores; 64-column tiles (two CTAs per 128 environments) while 128-column tiles would not fill the SMs
+    // the heads on the tensor cores; 64-column tiles (critic and actor in separate CTAs) while 128-column tiles would not fill the SMs
     TCArgs t;
-    t.E = h.E; t.K = p->K; t.chunks = p->tc_chunks; t.emb = emb; t.b1 = p->d_b1; t.h1 = p->d_h1;
+    t.h = h; t.chunks = p->tc_chunks; t.w2tc = p->d_w2tc;
     const int gx = (h.E + TC_M - 1) / TC_M;
     static thread_local bool tc_attr[16] = {false};
     if (!tc_attr[p->device & 15]) {
-      PCK(cudaFuncSetAttribute(evac_policy_l1_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCShape<64>::SMEM_BYTES));
-      PCK(cudaFuncSetAttribute(evac_policy_l1_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCShape<128>::SMEM_BYTES));
+      PCK(cudaFuncSetAttribute(evac_policy_heads_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCShape<64>::SMEM_BYTES));
+      PCK(cudaFuncSetAttribute(evac_policy_heads_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCShape<128>::SMEM_BYTES));
       tc_attr[p->device & 15] = true;
     }
-    if (gx < 2 * 148) { t.w1tc = p->d_w1tc64; evac_policy_l1_tc_kernel<64><<<dim3(gx, 2), TC_THREADS, TCShape<64>::SMEM_BYTES, st>>>(t); }
-    else { t.w1tc = p->d_w1tc128; evac_policy_l1_tc_kernel<128><<<dim3(gx, 1), TC_THREADS, TCShape<128>::SMEM_BYTES, st>>>(t); }
+    if (gx < 2 * 148) { t.w1tc = p->d_w1tc64; evac_policy_heads_tc_kernel<64><<<dim3(gx, 2), TC_THREADS, TCShape<64>::SMEM_BYTES, st>>>(t); }
+    else { t.w1tc = p->d_w1tc128; evac_policy_heads_tc_kernel<128><<<dim3(gx, 1), TC_THREADS, TCShape<128>::SMEM_BYTES, st>>>(t); }
     PCK(cudaGetLastError());
     p->launches++;
-    h.h1_in = p->d_h1;
+    return EVAC_OK;
   }
   static thread_local size_t hattr[16] = {0};
   if (p->heads_smem > 48 * 1024 && hattr[p->device & 15] < p->heads_smem) {

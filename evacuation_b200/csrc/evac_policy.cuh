@@ -433,7 +433,6 @@ constexpr size_t HD_SMEM_FLOATS = HD_STAGES * HD_KC * HD_COLS + HD_STAGES * HD_T
 struct HArgs {
   int E, K, K16, NH, A;          // K = S * D inputs, K16 = K rounded up to the chunk
   const float* emb;              // [E, K]
-  const float* h1_in;            // optional [E, 128]: tanh(layer 1) already computed (evac_policy_l1_tc_kernel) -> layer 1 is skipped here
   const float* w1t;              // [K16, 128]  column o < 64: critic.0.weight[o], 64 <= o: actor_mean.0.weight[o - 64] (zero padded)
   const float* b1;               // [128]
   const float* w2t;              // [64, 128]   row k, column o: (critic|actor).2.weight[o % 64][k] of o's own head (zero padded)
@@ -454,6 +453,43 @@ struct HArgs {
   const unsigned long long* offset_dev;
   long long env_offset;
 };
+
+// value + Normal(mean, exp(logstd)): sample / log-probability / entropy of environment e [rpo_linear_agent_network.py:47-61];
+// o = {value, mean[0], mean[1], mean[2]}.  `critic` / `actor` select which half is written (the tensor-core kernel splits the
+// two heads over two CTAs for small batches).
+__device__ __forceinline__ void heads_finish(const HArgs& a, int e, const float* o, bool critic, bool actor) {
+  if (critic && a.value) a.value[e] = o[0];
+  if (!actor) return;
+  const uint32_t env_g = (uint32_t)(a.env_offset + e);
+  float lp = 0.f, ent = 0.f;
+  const unsigned long long off = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
+  const evac::Philox4 r = evac::philox4x32_10(env_g, (uint32_t)off, (uint32_t)(off >> 32), 0x504F4C49u, a.seed_lo, a.seed_hi);
+  const uint32_t words[4] = {r.x, r.y, r.z, r.w};
+  for (int c = 0; c < a.A; ++c) {
+    const float mu = o[1 + c];
+    const float ls = a.logstd[c], sd = expf(ls);
+    float act = mu;
+    if (a.given_action != nullptr) act = a.given_action[(size_t)e * a.A + c];
+    else if (a.sample) {
+      // Box-Muller on two 24-bit uniforms in (0, 1): pair (0, 1) -> components 0 and 1, pair (2, 3) -> component 2
+      const int p = (c >> 1) * 2;
+      const float u1 = ((float)(words[p] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+      const float u2 = ((float)(words[p + 1] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+      const float rad = sqrtf(-2.f * logf(u1));
+      float sn, cs;
+      sincosf(6.28318530717958647692f * u2, &sn, &cs);
+      act = fmaf(sd, rad * ((c & 1) ? sn : cs), mu);
+    }
+    const float z = (act - mu) / sd;
+    lp += -0.5f * z * z - ls - 0.918938533204672741780f;
+    ent += 0.5f + 0.918938533204672741780f + ls;
+    if (a.mean) a.mean[(size_t)e * a.A + c] = mu;
+    if (a.action) a.action[(size_t)e * a.A + c] = act;
+    if (a.action_clipped) a.action_clipped[(size_t)e * a.A + c] = min_nan(max_nan(act, -1.f), 1.f);
+  }
+  if (a.logprob) a.logprob[e] = lp;
+  if (a.entropy) a.entropy[e] = ent;
+}
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int src_bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -546,15 +582,7 @@ __global__ void __launch_bounds__(HD_THREADS, 2) evac_policy_heads_kernel(const 
 
   float acc[8][8];
   // ---- layer 1
-  if (a.h1_in != nullptr) {   // computed on the tensor cores: stage the CTA's rows of H1 next to the layer-2 weights
-    for (int v = tid; v < HD_HS * HD_COLS / 4; v += HD_THREADS) cp_async16(w2s + 4 * v, a.w2t + 4 * v, 16);
-    for (int v = tid; v < HD_TM * HD_COLS / 4; v += HD_THREADS) {
-      const int r = v / (HD_COLS / 4), q = v - r * (HD_COLS / 4);
-      cp_async16(h1 + r * HD_H1S + 4 * q, a.h1_in + (size_t)(e0 + min(r, ne - 1)) * HD_COLS + 4 * q, 16);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-  } else {
+  {
     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
     if (kg == 0) { ba = *reinterpret_cast<const float4*>(a.b1 + 4 * cq); bb = *reinterpret_cast<const float4*>(a.b1 + HD_HS + 4 * cq); }
 #pragma unroll
@@ -642,40 +670,8 @@ __global__ void __launch_bounds__(HD_THREADS, 2) evac_policy_heads_kernel(const 
     o3[el * 4 + r] = s;   // A <= 3 (checked on the host)
   }
   __syncthreads();
-  // ---- Normal(mean, exp(logstd)): sample / log-probability / entropy [rpo_linear_agent_network.py:47-61]
-  if (tid < ne) {
-    const int e = e0 + tid;
-    const uint32_t env_g = (uint32_t)(a.env_offset + e);
-    if (a.value) a.value[e] = o3[tid * 4];
-    float lp = 0.f, ent = 0.f;
-    const unsigned long long off = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
-    const evac::Philox4 r = evac::philox4x32_10(env_g, (uint32_t)off, (uint32_t)(off >> 32), 0x504F4C49u, a.seed_lo, a.seed_hi);
-    const uint32_t words[4] = {r.x, r.y, r.z, r.w};
-    for (int c = 0; c < a.A; ++c) {
-      const float mu = o3[tid * 4 + 1 + c];
-      const float ls = a.logstd[c], sd = expf(ls);
-      float act = mu;
-      if (a.given_action != nullptr) act = a.given_action[(size_t)e * a.A + c];
-      else if (a.sample) {
-        // Box-Muller on two 24-bit uniforms in (0, 1): pair (0, 1) -> components 0 and 1, pair (2, 3) -> component 2
-        const int p = (c >> 1) * 2;
-        const float u1 = ((float)(words[p] >> 8) + 0.5f) * 5.9604644775390625e-08f;
-        const float u2 = ((float)(words[p + 1] >> 8) + 0.5f) * 5.9604644775390625e-08f;
-        const float rad = sqrtf(-2.f * logf(u1));
-        float sn, cs;
-        sincosf(6.28318530717958647692f * u2, &sn, &cs);
-        act = fmaf(sd, rad * ((c & 1) ? sn : cs), mu);
-      }
-      const float z = (act - mu) / sd;
-      lp += -0.5f * z * z - ls - 0.918938533204672741780f;
-      ent += 0.5f + 0.918938533204672741780f + ls;
-      if (a.mean) a.mean[(size_t)e * a.A + c] = mu;
-      if (a.action) a.action[(size_t)e * a.A + c] = act;
-      if (a.action_clipped) a.action_clipped[(size_t)e * a.A + c] = min_nan(max_nan(act, -1.f), 1.f);
-    }
-    if (a.logprob) a.logprob[e] = lp;
-    if (a.entropy) a.entropy[e] = ent;
-  }
+  // ---- Normal(mean, exp(logstd)): sample / log-probability / entropy
+  if (tid < ne) heads_finish(a, e0 + tid, o3 + tid * 4, true, true);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -1,55 +1,70 @@
-// Layer 1 of the policy heads on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+// The policy heads (critic | actor MLPs, Normal sampling) on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
 //
 //   H1[E, 128] = tanh( X[E, K] * W1[K, 128] + b1 )        X = transformer embedding (K = S * D = 372 at the reference shape),
-//                                                         W1 = [critic.0.weight^T | actor_mean.0.weight^T]
-//   [src/agents/networks/rpo_linear_agent_network.py:23-42 -- the one dense contraction on the rollout path]
+//   H2 = tanh( H1 * W2 + b2 ) per head (64 x 64)          W1 = [critic.0.weight^T | actor_mean.0.weight^T]
+//   value / mean = H2 * W3 + b3, Normal(mean, exp(logstd)) sample / log-probability / entropy
+//   [src/agents/networks/rpo_linear_agent_network.py:23-61 -- layer 1 is the one large dense contraction on the rollout path]
 //
-// One CTA = 128 environments x NT columns (NT = 64: two CTAs per 128 environments, for batches that would otherwise leave
-// SMs idle; NT = 128 for large batches); K in chunks of 32 (one 128-byte swizzle row of float32).  float32 fidelity from
-// kind::tf32 MMAs (10-bit mantissa operands) by the 3xTF32 split:  x = xh + xl, w = wh + wl (xh / wh = the value with the
-// 13 low mantissa bits cleared, xl / wl = the float32 remainder, truncated by the tensor core to its top 10 bits):
+// One CTA = 128 environments x NT hidden columns: NT = 128 (both heads) for large batches, NT = 64 (blockIdx.y = 0: critic,
+// 1: actor -- the heads share nothing after the embedding) for batches that would otherwise leave SMs idle.
+//
+// Layer 1: K in chunks of 32 (one 128-byte swizzle row of float32).  float32 fidelity from kind::tf32 MMAs (10-bit mantissa
+// operands) by the 3xTF32 split:  x = xh + xl, w = wh + wl (xh / wh = the value rounded to 10 mantissa bits,
+// xl / wl = the float32 remainder, truncated by the tensor core to its top 10 bits):
 //   x w  ~=  xh wh + xl wh + xh wl          (error ~2^-21 per product; the xl wl term is below float32 resolution)
 // accumulated in float32 in tensor memory.  Per chunk and CTA: 4 k-steps (UMMA_K = 8) x 3 products = 12 tcgen05.mma
 // (M = 128, N = NT) issued by ONE thread of a dedicated warp; operands in shared memory in the canonical K-major
 // SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row-in-atom) -- X is split and laid out by the four
 // producer warps (global loads of chunk c + 1 in flight while chunk c is stored), the weight tiles are split and swizzled
 // once on the host (evac_policy_load_weights) and arrive as ONE bulk copy per chunk (cp.async.bulk + mbarrier
-// complete_tx).  Ring of TC_STAGES stages: full[s] (128 producer arrivals + the bulk copy's bytes) / empty[s]
-// (tcgen05.commit).  Epilogue: tcgen05.ld 32x32b (warp w owns TMEM lanes 32w .. 32w + 31 = environments), + bias, tanh,
-// float4 stores of H1; evac_policy_heads_kernel continues from H1 (HArgs::h1_in).
+// complete_tx).  Ring of STAGES stages: full[s] (128 producer arrivals + the bulk copy's bytes) / empty[s] (tcgen05.commit).
+//
+// Layer 2 stays on chip: epilogue 1 (tcgen05.ld 32x32b: warp w owns TMEM lanes 32w .. 32w + 31 = environments; + bias, tanh)
+// writes H1 -- split into hi / lo again -- as the A operand tiles of the second product into the drained ring, the layer-2
+// weight tiles (32 KB per head) arrive by one more bulk copy, 24 MMAs (N = 64) per head accumulate into further TMEM
+// columns.  Epilogue 2: + bias, tanh, the (1 + A) x 64 output layer as per-thread dot products straight from the TMEM
+// loads, then the sampling tail shared with the CUDA-core kernel (heads_finish).  H1 / H2 never touch global memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace evacp {
 
 constexpr int TC_M = 128, TC_KC = 32;
 constexpr int TC_COLS = 128;                                 // = HD_COLS
-constexpr int TC_THREADS = 160;                              // warps 0-3: producers + epilogue, warp 4: MMA issue + TMEM allocation
-constexpr int TC_XTILE_BYTES = TC_M * TC_KC * 4;             // 16 KB: one X tile (128 rows x 128 bytes)
+constexpr int TC_THREADS = 160;                              // warps 0-3: producers + epilogues, warp 4: MMA issue + TMEM allocation
+constexpr int TC_XTILE_BYTES = TC_M * TC_KC * 4;             // 16 KB: one A tile (128 rows x 128 bytes)
+constexpr int TC_W2_HEAD_BYTES = 2 * 2 * HD_HS * TC_KC * 4;  // layer-2 weights of one head: 2 k-chunks x (hi | lo) x 64 rows x 128 bytes
 template <int NT> struct TCShape {
-  static constexpr int WTILE_BYTES = NT * TC_KC * 4;         // one W tile (NT rows x 128 bytes)
+  static constexpr int WTILE_BYTES = NT * TC_KC * 4;         // one W1 tile (NT rows x 128 bytes)
   static constexpr int STAGE_BYTES = 2 * TC_XTILE_BYTES + 2 * WTILE_BYTES;   // X hi | X lo | W hi | W lo
   static constexpr int STAGES = NT == 64 ? 4 : 3;
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int HEADS = NT / HD_HS;                   // heads handled by one CTA
+  static constexpr int A2_BYTES = (NT / TC_KC) * 2 * TC_XTILE_BYTES;         // H1 as A operand: NT / 32 k-chunks x (hi | lo)
+  static constexpr int W2_BYTES = HEADS * TC_W2_HEAD_BYTES;
+  static_assert(A2_BYTES + W2_BYTES <= STAGES * STAGE_BYTES, "layer-2 operands reuse the drained ring");
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int CONST_FLOATS = 2 * TC_COLS + 4 * HD_HS + 8;           // b1 | b2 | w3 | b3 | logstd
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + BAR_BYTES + CONST_FLOATS * 4;
 };
 
 struct TCArgs {
-  int E, K, chunks;        // chunks = ceil(K / 32)
-  const float* emb;        // [E, K] float32, rows 16-byte aligned (K % 4 == 0)
+  HArgs h;                 // shapes, biases, output layer, outputs, sampling (w1t / w2t unused here)
+  int chunks;              // ceil(K / 32)
   const float* w1tc;       // [chunks][128 / NT][hi tile | lo tile], each tile NT (column) rows x 32 k, swizzled
-  const float* b1;         // [128]
-  float* h1;               // [E, 128] out
+  const float* w2tc;       // [head][k-chunk (2)][hi tile | lo tile], each tile 64 (column) rows x 32 k, swizzled
 };
 
 // byte offset of element (row r, 16-byte chunk c4) inside a K-major SWIZZLE_128B tile
 __host__ __device__ __forceinline__ uint32_t tc_swizzle(int r, int c4) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c4 ^ (r & 7)) << 4)); }
-// the value with its 13 low mantissa bits cleared: exactly representable as TF32
+// the nearest value with 13 zero low mantissa bits (exactly representable as TF32); the remainder x - tc_hi(x) then has at most
+// 12 significant bits, of which the tensor core keeps 11
 __host__ __device__ __forceinline__ float tc_hi(float x) {
 #ifdef __CUDA_ARCH__
-  return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 #else
-  uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; float y; memcpy(&y, &u, 4); return y;
+  uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xFFFFE000u; float y; memcpy(&y, &u, 4); return y;
 #endif
 }
 
@@ -62,6 +77,9 @@ __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {  // raises the transaction count, no arrival
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -94,38 +112,67 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {  // implies tcgen05.f
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tc_bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem_u32(dst_smem)), "l"(src),
+               "r"(bytes), "r"(tc_smem_u32(bar))
+               : "memory");
+}
+// 32 consecutive TMEM columns of this thread's lane (32x32b: warp w reads lanes 32 w .. 32 w + 31), complete on return
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, "
+      "%29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <int NT>
-__global__ void __launch_bounds__(TC_THREADS, 1) evac_policy_l1_tc_kernel(const __grid_constant__ TCArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) evac_policy_heads_tc_kernel(const __grid_constant__ TCArgs a) {
   using SH = TCShape<NT>;
-  constexpr int STAGES = SH::STAGES;
+  constexpr int STAGES = SH::STAGES, HEADS = SH::HEADS;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024-byte aligned
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * SH::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* accum = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  uint64_t* accum = empty + STAGES;      // accum[0]: layer-1 accumulators complete, accum[1]: layer-2 accumulators complete
+  uint64_t* full2 = accum + 2;           // layer-2 operands (H1 tiles + weight tiles) in place
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full2 + 1);
+  float* cst = reinterpret_cast<float*>(smem + STAGES * SH::STAGE_BYTES + SH::BAR_BYTES);
+  float* b1s = cst, *b2s = cst + TC_COLS, *w3s = cst + 2 * TC_COLS, *b3s = w3s + 4 * HD_HS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int e0 = blockIdx.x * TC_M;
-  const int ny = TC_COLS / NT, y = blockIdx.y;
+  const int ny = TC_COLS / NT, y = blockIdx.y;   // NT = 64: y = 0 critic, y = 1 actor
+  const HArgs& h = a.h;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { tc_mbar_init(&full[s], 128); tc_mbar_init(&empty[s], 1); }
-    tc_mbar_init(accum, 1);
+    tc_mbar_init(&accum[0], 1); tc_mbar_init(&accum[1], 1); tc_mbar_init(full2, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {  // NT TMEM columns of float32 accumulators (power of two >= 32), one warp allocates and later frees
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "n"(NT) : "memory");
+  if (warp == 4) {  // 2 NT TMEM columns of float32 accumulators (layer 1 | layer 2), one warp allocates and later frees
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "n"(2 * NT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = tid; i < TC_COLS; i += TC_THREADS) { b1s[i] = h.b1[i]; b2s[i] = h.b2[i]; }
+  for (int i = tid; i < 4 * HD_HS; i += TC_THREADS) w3s[i] = i < (1 + h.A) * HD_HS ? h.w3[i] : 0.f;
+  if (tid < 4) b3s[tid] = tid < 1 + h.A ? h.b3[tid] : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  uint8_t* a2 = smem;                       // H1 operand tiles: k-chunk j at j * 32 KB (hi | lo)
+  uint8_t* w2 = smem + SH::A2_BYTES;        // layer-2 weight tiles of this CTA's head(s)
 
   if (warp == 4) {
-    // ---- MMA issue: one thread, 12 tcgen05.mma per chunk, stage handed back through tcgen05.commit
     if (lane == 0) {
-      constexpr uint32_t IDESC = tc_idesc<NT>();
+      // ---- layer 1: 12 tcgen05.mma per chunk, stage handed back through tcgen05.commit
+      constexpr uint32_t IDESC1 = tc_idesc<NT>(), IDESC2 = tc_idesc<HD_HS>();
       for (int c = 0; c < a.chunks; ++c) {
         const int s = c % STAGES;
         tc_mbar_wait(&full[s], (uint32_t)((c / STAGES) & 1));
@@ -135,24 +182,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) evac_policy_l1_tc_kernel(const 
         for (int k = 0; k < TC_KC / 8; ++k) {  // UMMA_K = 8 float32 = 32 bytes along the swizzled row
           const uint64_t xh = tc_desc(base + k * 32), xl = tc_desc(base + TC_XTILE_BYTES + k * 32);
           const uint64_t wh = tc_desc(base + 2 * TC_XTILE_BYTES + k * 32), wl = tc_desc(base + 2 * TC_XTILE_BYTES + SH::WTILE_BYTES + k * 32);
-          tc_mma(tmem, xh, wh, IDESC, (c > 0 || k > 0) ? 1u : 0u);
-          tc_mma(tmem, xl, wh, IDESC, 1u);
-          tc_mma(tmem, xh, wl, IDESC, 1u);
+          tc_mma(tmem, xh, wh, IDESC1, (c > 0 || k > 0) ? 1u : 0u);
+          tc_mma(tmem, xl, wh, IDESC1, 1u);
+          tc_mma(tmem, xh, wl, IDESC1, 1u);
         }
         tc_commit(&empty[s]);
       }
-      tc_commit(accum);
+      tc_commit(&accum[0]);
+      // ---- layer 2: per head [128 x 64] x [64 x 64], operands written by epilogue 1 / the second bulk copy
+      tc_mbar_wait(full2, 0u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int hd = 0; hd < HEADS; ++hd) {
+#pragma unroll
+        for (int c = 0; c < HD_HS / TC_KC; ++c) {
+          const uint32_t ab = tc_smem_u32(a2 + (hd * (HD_HS / TC_KC) + c) * 2 * TC_XTILE_BYTES);
+          const uint32_t wb = tc_smem_u32(w2 + hd * TC_W2_HEAD_BYTES + c * (2 * HD_HS * TC_KC * 4));
+#pragma unroll
+          for (int k = 0; k < TC_KC / 8; ++k) {
+            const uint64_t xh = tc_desc(ab + k * 32), xl = tc_desc(ab + TC_XTILE_BYTES + k * 32);
+            const uint64_t wh = tc_desc(wb + k * 32), wl = tc_desc(wb + HD_HS * TC_KC * 4 + k * 32);
+            const uint32_t d = tmem + (uint32_t)(NT + hd * HD_HS);
+            tc_mma(d, xh, wh, IDESC2, (c > 0 || k > 0) ? 1u : 0u);
+            tc_mma(d, xl, wh, IDESC2, 1u);
+            tc_mma(d, xh, wl, IDESC2, 1u);
+          }
+        }
+      }
+      tc_commit(&accum[1]);
     }
   } else {
     // ---- producers: split X into hi / lo tiles (registers hold chunk c + 1 while chunk c is stored), request the weight tiles
-    const int kq = a.K >> 2;  // float4 per row of X
+    const int kq = h.K >> 2;  // float4 per row of X
     auto load_x = [&](int c, float4 (&x)[8]) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int idx = i * 128 + tid, r = idx >> 3, c4 = idx & 7;
         const int e = e0 + r, q = c * 8 + c4;
         x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < a.E && q < kq) x[i] = __ldg(reinterpret_cast<const float4*>(a.emb + (size_t)e * a.K + 4 * q));
+        if (e < h.E && q < kq) x[i] = __ldg(reinterpret_cast<const float4*>(h.emb + (size_t)e * h.K + 4 * q));
       }
     };
     float4 xr[8], xn[8];
@@ -178,51 +246,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) evac_policy_l1_tc_kernel(const 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core (async proxy)
       if (tid == 0) {
         tc_mbar_arrive_expect_tx(&full[s], 2 * SH::WTILE_BYTES);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem_u32(st + 2 * TC_XTILE_BYTES)),
-                     "l"(a.w1tc + ((size_t)c * ny + y) * (2 * SH::WTILE_BYTES / 4)), "r"(2 * SH::WTILE_BYTES), "r"(tc_smem_u32(&full[s]))
-                     : "memory");
+        tc_bulk_load(st + 2 * TC_XTILE_BYTES, a.w1tc + ((size_t)c * ny + y) * (2 * SH::WTILE_BYTES / 4), 2 * SH::WTILE_BYTES, &full[s]);
       } else {
         tc_mbar_arrive(&full[s]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) xr[i] = xn[i];
     }
-    // ---- epilogue: TMEM lane = environment, column = hidden unit
-    tc_mbar_wait(accum, 0u);
+    // ---- epilogue 1: TMEM lane = environment (this thread's row), column = hidden unit -> H1 operand tiles of layer 2
+    tc_mbar_wait(&accum[0], 0u);           // every layer-1 MMA has completed: accumulators final, the ring is free
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int e = e0 + tid;
+    if (tid == 0) {
+      tc_mbar_expect_tx(full2, SH::W2_BYTES);
+      tc_bulk_load(w2, a.w2tc + (size_t)(NT == 64 ? y : 0) * (TC_W2_HEAD_BYTES / 4), SH::W2_BYTES, full2);
+    }
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int j = 0; j < NT / 32; ++j) {
       uint32_t v[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, "
-          "%29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-            "=r"(v[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (e < a.E) {
-        const int col0 = y * NT + j * 32;
-        float* dst = a.h1 + (size_t)e * TC_COLS + col0;
+      tc_tmem_ld32(trow + (uint32_t)(j * 32), v);
+      uint8_t* tile = a2 + j * 2 * TC_XTILE_BYTES;
+      const float* bj = b1s + y * NT + j * 32;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(a.b1 + col0 + i));
-          *reinterpret_cast<float4*>(dst + i) = make_float4(tanhf(__uint_as_float(v[i]) + b.x), tanhf(__uint_as_float(v[i + 1]) + b.y),
-                                                            tanhf(__uint_as_float(v[i + 2]) + b.z), tanhf(__uint_as_float(v[i + 3]) + b.w));
+      for (int i = 0; i < 32; i += 4) {
+        const float4 t = make_float4(tanhf(__uint_as_float(v[i]) + bj[i]), tanhf(__uint_as_float(v[i + 1]) + bj[i + 1]),
+                                     tanhf(__uint_as_float(v[i + 2]) + bj[i + 2]), tanhf(__uint_as_float(v[i + 3]) + bj[i + 3]));
+        float4 hi, lo;
+        hi.x = tc_hi(t.x); lo.x = t.x - hi.x;
+        hi.y = tc_hi(t.y); lo.y = t.y - hi.y;
+        hi.z = tc_hi(t.z); lo.z = t.z - hi.z;
+        hi.w = tc_hi(t.w); lo.w = t.w - hi.w;
+        const uint32_t off = tc_swizzle(tid, i >> 2);
+        *reinterpret_cast<float4*>(tile + off) = hi;
+        *reinterpret_cast<float4*>(tile + TC_XTILE_BYTES + off) = lo;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_mbar_arrive(full2);
+    // ---- epilogue 2: H2 = tanh(. + b2) and the output layer as dot products over the TMEM loads, then the sampling tail
+    tc_mbar_wait(&accum[1], 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float o[4] = {b3s[0], b3s[1], b3s[2], b3s[3]};
+#pragma unroll 1
+    for (int j = 0; j < NT / 32; ++j) {
+      uint32_t v[32];
+      tc_tmem_ld32(trow + (uint32_t)(NT + j * 32), v);
+      const int col0 = y * NT + j * 32;               // hidden column of v[0]: < 64 critic, >= 64 actor
+      const float* bj = b2s + col0;
+      if (col0 < HD_HS) {
+        const float* w = w3s + col0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[0] = fmaf(tanhf(__uint_as_float(v[i]) + bj[i]), w[i], o[0]);
+      } else {
+        const float* w = w3s + HD_HS + (col0 - HD_HS);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float t = tanhf(__uint_as_float(v[i]) + bj[i]);
+          o[1] = fmaf(t, w[i], o[1]); o[2] = fmaf(t, w[HD_HS + i], o[2]); o[3] = fmaf(t, w[2 * HD_HS + i], o[3]);
         }
       }
     }
+    const int e = e0 + tid;
+    if (e < h.E) heads_finish(h, e, o, NT == 128 || y == 0, NT == 128 || y == 1);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NT) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NT) : "memory");
   }
 }
 

@@ -117,7 +117,7 @@ def test_fused_policy_shapes_vs_torch(n_ped, d_model, kw):
 
 @pytest.mark.parametrize("E", [5, 129, 4096, 38000])
 def test_heads_on_tensor_cores_match_the_cuda_core_path_and_float64(E, monkeypatch):
-    """Layer 1 of the heads ([E x 372] x [372 x 128]) runs as 3xTF32 tcgen05 MMAs (csrc/evac_policy_tc.cuh; 64-column tiles
+    """The heads ([E x 372] x [372 x 128], then 64 x 64 per head) run as 3xTF32 tcgen05 MMAs (csrc/evac_policy_tc.cuh; 64-column tiles
     below 296 row tiles, 128-column tiles above: E = 38000).  EVAC_POLICY_TC=0 (read at evac_policy_create) keeps it on the
     CUDA cores.  Both must sit within float32 rounding of a float64 evaluation of the heads on the kernel's own embedding
     [rpo_linear_agent_network.py:23-42]."""
@@ -147,7 +147,7 @@ def test_heads_on_tensor_cores_match_the_cuda_core_path_and_float64(E, monkeypat
         mean64, val64 = net64.actor_mean(e64), net64.critic(e64).flatten()
     for tc in ("1", "0"):
         assert float((outs[tc][1].double() - mean64).abs().max()) < 2e-6, tc
-        assert float((outs[tc][2].double() - val64).abs().max() / val64.abs().max().clamp_min(1.0)) < 4e-6, tc
+        assert float((outs[tc][2].double() - val64).abs().max() / val64.abs().max().clamp_min(1.0)) < 6e-6, tc
     # the sampled action is mean + std * noise with noise keyed by (seed, call, env): identical streams on both paths
     np.testing.assert_allclose(outs["1"][3].cpu().numpy(), outs["0"][3].cpu().numpy(), rtol=0, atol=2e-6)
     np.testing.assert_allclose(outs["1"][4].cpu().numpy(), outs["0"][4].cpu().numpy(), rtol=0, atol=2e-5)

@@ -13,7 +13,6 @@
 #include "../../include/evac_b200.h"
 #include "evac_kernels.cuh"
 #include "evac_warp.cuh"
-#include "evac_halfwarp.cuh"
 
 using namespace evac;
 
@@ -76,7 +75,6 @@ struct EvacHandle {
   int cluster = 1;               // > 1: one environment per thread-block cluster of this many 1024 x 4 CTAs (N > 4096, evac_cluster.cuh)
   bool warp_kernel = true;       // N <= 64 fp32: evac_warp_kernel (false: the generic kernel, EVAC_WARP_KERNEL=generic)
   int warps_per_cta = 1;         // environments per CTA of evac_warp_kernel (EVAC_WARP_WPC = 1 | 2 | 4 | 8)
-  bool half_warp = false;        // two environments per warp (evac_halfwarp.cuh; EVAC_WARP_KERNEL=half | warp)
 };
 
 // smallest double b such that sqrt(v) >= t for every v >= b  <=>  (v < b) == (sqrt(v) < t)
@@ -220,15 +218,6 @@ static void launch_warp_t(const KArgs<float>& a, cudaStream_t st) {
   else evac_warp_kernel<WMODE_GENERIC, WPC><<<grid, 32 * WPC, 0, st>>>(a);
 }
 static int launch_warp(EvacHandle* h, const KArgs<float>& a, cudaStream_t st) {
-  if (h->half_warp && a.cells_x == 0) {  // (the strip-culling variant only exists in the one-warp kernel)
-    const int grid = (a.E + 1) / 2;
-    if (a.positions == POS_REL && a.statuses == STAT_OHE && a.obs_type == OBS_BOX) evac_hw_kernel<WMODE_REL_OHE_BOX><<<grid, 32, 0, st>>>(a);
-    else if (a.positions == POS_GRAV) evac_hw_kernel<WMODE_GRAV><<<grid, 32, 0, st>>>(a);
-    else evac_hw_kernel<WMODE_GENERIC><<<grid, 32, 0, st>>>(a);
-    CK(cudaGetLastError());
-    h->launches++;
-    return EVAC_OK;
-  }
   switch (h->warps_per_cta) {  // measured on B200 (tools/wpc_sweep.sh): 1 is the fastest at 4096 envs (14.0 / 14.4 / 14.4 / 14.9 us)
     case 2: launch_warp_t<2>(a, st); break;
     case 4: launch_warp_t<4>(a, st); break;
@@ -364,7 +353,7 @@ int evac_create(const EvacConfig* cfg, int32_t num_envs, int32_t device, uint64_
     h->cluster = want;
     if (h->cluster > 1) { h->threads = 1024; h->ppt = 4; }
   }
-  { const char* wk = getenv("EVAC_WARP_KERNEL"); h->warp_kernel = !(wk && strcmp(wk, "generic") == 0); h->half_warp = wk && strcmp(wk, "half") == 0; }
+  { const char* wk = getenv("EVAC_WARP_KERNEL"); h->warp_kernel = !(wk && strcmp(wk, "generic") == 0); }
   { const char* wp = getenv("EVAC_WARP_WPC"); if (wp) h->warps_per_cta = atoi(wp); }
   if (h->N > 64 && h->threads > 32 && h->prec == EVAC_PREC_F32 && cfg->neighbor_search != EVAC_SEARCH_BRUTE) {
     // cell edge >= (1 + 1e-4) x vision radius: two pedestrians closer than the radius always sit in the same or

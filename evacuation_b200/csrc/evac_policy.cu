@@ -343,14 +343,22 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
     TCArgs t;
     t.h = h; t.chunks = p->tc_chunks; t.w2tc = p->d_w2tc;
     const int gx = (h.E + TC_M - 1) / TC_M;
+    // shapes: 64 columns x 4 stages (critic and actor in separate CTAs) while 128-column tiles would not fill the SMs, 128 columns
+    // x 3 stages beyond (X is read once).  Measured per 8192 / 20 000 / 65 536 envs: 20.3 / 49.3 / 121.5 us (64x4), 29.7 / 50.4 /
+    // 105.0 us (128x3); 64 columns x 2 stages with two CTAs per SM: 24.6 / 53.6 / 113.1 us.  EVAC_POLICY_TC_SHAPE=64x4 | 128x3: A/B.
+    auto k64 = evac_policy_heads_tc_kernel<64, 4, 2, 1>;
+    auto k128 = evac_policy_heads_tc_kernel<128, 3, 2, 1>;
+    using S64 = TCShape<64, 4, 2>; using S128 = TCShape<128, 3, 2>;
     static thread_local bool tc_attr[16] = {false};
     if (!tc_attr[p->device & 15]) {
-      PCK(cudaFuncSetAttribute(evac_policy_heads_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCShape<64>::SMEM_BYTES));
-      PCK(cudaFuncSetAttribute(evac_policy_heads_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCShape<128>::SMEM_BYTES));
+      PCK(cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S64::SMEM_BYTES));
+      PCK(cudaFuncSetAttribute(k128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S128::SMEM_BYTES));
       tc_attr[p->device & 15] = true;
     }
-    if (gx < 2 * 148) { t.w1tc = p->d_w1tc64; evac_policy_heads_tc_kernel<64><<<dim3(gx, 2), TC_THREADS, TCShape<64>::SMEM_BYTES, st>>>(t); }
-    else { t.w1tc = p->d_w1tc128; evac_policy_heads_tc_kernel<128><<<dim3(gx, 1), TC_THREADS, TCShape<128>::SMEM_BYTES, st>>>(t); }
+    bool wide = gx >= 2 * 148;
+    if (const char* sh = getenv("EVAC_POLICY_TC_SHAPE")) wide = strcmp(sh, "128x3") == 0 ? true : strcmp(sh, "64x4") == 0 ? false : wide;
+    if (!wide) { t.w1tc = p->d_w1tc64; k64<<<dim3(gx, 2), TC_THREADS, S64::SMEM_BYTES, st>>>(t); }
+    else { t.w1tc = p->d_w1tc128; k128<<<dim3(gx, 1), TC_THREADS, S128::SMEM_BYTES, st>>>(t); }
     PCK(cudaGetLastError());
     p->launches++;
     return EVAC_OK;

@@ -14,10 +14,10 @@
 //   x w  ~=  xh wh + xl wh + xh wl          (error ~2^-21 per product; the xl wl term is below float32 resolution)
 // accumulated in float32 in tensor memory.  Per chunk and CTA: 4 k-steps (UMMA_K = 8) x 3 products = 12 tcgen05.mma
 // (M = 128, N = NT) issued by ONE thread of a dedicated warp; operands in shared memory in the canonical K-major
-// SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row-in-atom) -- X is split and laid out by the four
-// producer warps (global loads of chunk c + 1 in flight while chunk c is stored), the weight tiles are split and swizzled
-// once on the host (evac_policy_load_weights) and arrive as ONE bulk copy per chunk (cp.async.bulk + mbarrier
-// complete_tx).  Ring of STAGES stages: full[s] (128 producer arrivals + the bulk copy's bytes) / empty[s] (tcgen05.commit).
+// SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row-in-atom) -- X arrives by cp.async straight into
+// the swizzled hi tile, two chunks ahead (the tensor core ignores the low mantissa bits itself), the four producer warps
+// only add the lo tile; the weight tiles are split and swizzled once on the host (evac_policy_load_weights) and arrive
+// as ONE bulk copy per chunk (cp.async.bulk + mbarrier complete_tx).  Ring of STAGES stages: full[s] (128 producer arrivals + the bulk copy's bytes) / empty[s] (tcgen05.commit).
 //
 // Layer 2 stays on chip: epilogue 1 (tcgen05.ld 32x32b: warp w owns TMEM lanes 32w .. 32w + 31 = environments; + bias, tanh)
 // writes H1 -- split into hi / lo again -- as the A operand tiles of the second product into the drained ring, the layer-2
@@ -36,10 +36,12 @@ constexpr int TC_COLS = 128;                                 // = HD_COLS
 constexpr int TC_THREADS = 160;                              // warps 0-3: producers + epilogues, warp 4: MMA issue + TMEM allocation
 constexpr int TC_XTILE_BYTES = TC_M * TC_KC * 4;             // 16 KB: one A tile (128 rows x 128 bytes)
 constexpr int TC_W2_HEAD_BYTES = 2 * 2 * HD_HS * TC_KC * 4;  // layer-2 weights of one head: 2 k-chunks x (hi | lo) x 64 rows x 128 bytes
-template <int NT> struct TCShape {
+// NT = hidden columns per CTA, ST = ring stages, AH = chunks of X in flight ahead of the one being finished (< ST)
+template <int NT, int ST, int AH> struct TCShape {
   static constexpr int WTILE_BYTES = NT * TC_KC * 4;         // one W1 tile (NT rows x 128 bytes)
   static constexpr int STAGE_BYTES = 2 * TC_XTILE_BYTES + 2 * WTILE_BYTES;   // X hi | X lo | W hi | W lo
-  static constexpr int STAGES = NT == 64 ? 4 : 3;
+  static constexpr int STAGES = ST, AHEAD = AH;
+  static_assert(AH >= 1 && AH < ST, "look-ahead must leave the stage being consumed alone");
   static constexpr int HEADS = NT / HD_HS;                   // heads handled by one CTA
   static constexpr int A2_BYTES = (NT / TC_KC) * 2 * TC_XTILE_BYTES;         // H1 as A operand: NT / 32 k-chunks x (hi | lo)
   static constexpr int W2_BYTES = HEADS * TC_W2_HEAD_BYTES;
@@ -67,6 +69,9 @@ __host__ __device__ __forceinline__ float tc_hi(float x) {
   uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xFFFFE000u; float y; memcpy(&y, &u, 4); return y;
 #endif
 }
+
+// the value as kind::tf32 reads it: the 13 low mantissa bits ignored
+__device__ __forceinline__ float tc_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
@@ -132,10 +137,10 @@ __device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int NT>
-__global__ void __launch_bounds__(TC_THREADS, 1) evac_policy_heads_tc_kernel(const __grid_constant__ TCArgs a) {
-  using SH = TCShape<NT>;
-  constexpr int STAGES = SH::STAGES, HEADS = SH::HEADS;
+template <int NT, int ST, int AH, int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(const __grid_constant__ TCArgs a) {
+  using SH = TCShape<NT, ST, AH>;
+  constexpr int STAGES = SH::STAGES, HEADS = SH::HEADS, TC_AHEAD = SH::AHEAD;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024-byte aligned
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * SH::STAGE_BYTES);
@@ -212,46 +217,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) evac_policy_heads_tc_kernel(con
       tc_commit(&accum[1]);
     }
   } else {
-    // ---- producers: split X into hi / lo tiles (registers hold chunk c + 1 while chunk c is stored), request the weight tiles
+    // ---- producers.  X travels global -> shared as raw float32 straight into the swizzled "hi" tile (cp.async, 16 bytes per
+    // request, TC_AHEAD chunks ahead): kind::tf32 ignores the 13 low mantissa bits of its operands, so the raw value IS
+    // xh = trunc(x) to the tensor core; each thread then reads back the eight float4 it requested itself, writes
+    // xl = x - trunc(x) into the "lo" tile and arrives.  The weight tiles of the same chunk ride on one bulk copy.
     const int kq = h.K >> 2;  // float4 per row of X
-    auto load_x = [&](int c, float4 (&x)[8]) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = i * 128 + tid, r = idx >> 3, c4 = idx & 7;
-        const int e = e0 + r, q = c * 8 + c4;
-        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < h.E && q < kq) x[i] = __ldg(reinterpret_cast<const float4*>(h.emb + (size_t)e * h.K + 4 * q));
-      }
-    };
-    float4 xr[8], xn[8];
-    load_x(0, xr);
-    for (int c = 0; c < a.chunks; ++c) {
+    auto request = [&](int c) {
       const int s = c % STAGES, use = c / STAGES;
-      if (c + 1 < a.chunks) load_x(c + 1, xn);
       if (use > 0) tc_mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));  // the MMAs that read this stage have completed
       uint8_t* st = smem + s * SH::STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int idx = i * 128 + tid, r = idx >> 3, c4 = idx & 7;
-        const float4 x = xr[i];
-        float4 hi, lo;
-        hi.x = tc_hi(x.x); lo.x = x.x - hi.x;
-        hi.y = tc_hi(x.y); lo.y = x.y - hi.y;
-        hi.z = tc_hi(x.z); lo.z = x.z - hi.z;
-        hi.w = tc_hi(x.w); lo.w = x.w - hi.w;
-        const uint32_t off = tc_swizzle(r, c4);
-        *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + TC_XTILE_BYTES + off) = lo;
+        const int e = e0 + r, q = c * 8 + c4;
+        const bool in = e < h.E && q < kq;
+        cp_async16(reinterpret_cast<float*>(st + tc_swizzle(r, c4)), h.emb + (in ? (size_t)e * h.K + 4 * q : (size_t)0), in ? 16 : 0);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core (async proxy)
       if (tid == 0) {
-        tc_mbar_arrive_expect_tx(&full[s], 2 * SH::WTILE_BYTES);
+        tc_mbar_expect_tx(&full[s], 2 * SH::WTILE_BYTES);
         tc_bulk_load(st + 2 * TC_XTILE_BYTES, a.w1tc + ((size_t)c * ny + y) * (2 * SH::WTILE_BYTES / 4), 2 * SH::WTILE_BYTES, &full[s]);
-      } else {
-        tc_mbar_arrive(&full[s]);
       }
+    };
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xr[i] = xn[i];
+    for (int c = 0; c < TC_AHEAD; ++c) {
+      if (c < a.chunks) request(c);
+      cp_async_commit();
+    }
+    for (int c = 0; c < a.chunks; ++c) {
+      if (c + TC_AHEAD < a.chunks) request(c + TC_AHEAD);
+      cp_async_commit();               // one group per iteration, empty or not: group index == chunk index
+      cp_async_wait<TC_AHEAD>();       // this thread's requests of chunk c have landed
+      uint8_t* st = smem + (c % STAGES) * SH::STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = i * 128 + tid, r = idx >> 3, c4 = idx & 7;
+        const uint32_t off = tc_swizzle(r, c4);
+        const float4 x = *reinterpret_cast<const float4*>(st + off);
+        *reinterpret_cast<float4*>(st + TC_XTILE_BYTES + off) =
+            make_float4(x.x - tc_trunc(x.x), x.y - tc_trunc(x.y), x.z - tc_trunc(x.z), x.w - tc_trunc(x.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async / generic-proxy stores -> visible to the tensor core (async proxy)
+      tc_mbar_arrive(&full[c % STAGES]);
     }
     // ---- epilogue 1: TMEM lane = environment (this thread's row), column = hidden unit -> H1 operand tiles of layer 2
     tc_mbar_wait(&accum[0], 0u);           // every layer-1 MMA has completed: accumulators final, the ring is free

@@ -19,7 +19,8 @@
 // only add the lo tile; the weight tiles are split and swizzled once on the host (evac_policy_load_weights) and arrive
 // as ONE bulk copy per chunk (cp.async.bulk + mbarrier complete_tx).  Ring of STAGES stages: full[s] (128 producer arrivals + the bulk copy's bytes) / empty[s] (tcgen05.commit).
 //
-// Layer 2 stays on chip: epilogue 1 (tcgen05.ld 32x32b: warp w owns TMEM lanes 32w .. 32w + 31 = environments; + bias, tanh)
+// Layer 2 stays on chip: epilogue 1 (tcgen05.ld 32x32b: eight warps, warp w reads TMEM lanes 32 (w % 4) .. = environments and half of
+// the columns; + bias, tanh)
 // writes H1 -- split into hi / lo again -- as the A operand tiles of the second product into the drained ring, the layer-2
 // weight tiles (32 KB per head) arrive by one more bulk copy, 24 MMAs (N = 64) per head accumulate into further TMEM
 // columns.  Epilogue 2: + bias, tanh, the (1 + A) x 64 output layer as per-thread dot products straight from the TMEM
@@ -33,7 +34,9 @@ namespace evacp {
 
 constexpr int TC_M = 128, TC_KC = 32;
 constexpr int TC_COLS = 128;                                 // = HD_COLS
-constexpr int TC_THREADS = 160;                              // warps 0-3: producers + epilogues, warp 4: MMA issue + TMEM allocation
+constexpr int TC_EW = 8;                                     // producer / epilogue warps: two per TMEM lane quarter (= two per scheduler)
+constexpr int TC_ET = 32 * TC_EW;                            // ... threads
+constexpr int TC_THREADS = TC_ET + 32;                       // + warp TC_EW: MMA issue + TMEM allocation
 constexpr int TC_XTILE_BYTES = TC_M * TC_KC * 4;             // 16 KB: one A tile (128 rows x 128 bytes)
 constexpr int TC_W2_HEAD_BYTES = 2 * 2 * HD_HS * TC_KC * 4;  // layer-2 weights of one head: 2 k-chunks x (hi | lo) x 64 rows x 128 bytes
 // NT = hidden columns per CTA, ST = ring stages, AH = chunks of X in flight ahead of the one being finished (< ST)
@@ -47,7 +50,7 @@ template <int NT, int ST, int AH> struct TCShape {
   static constexpr int W2_BYTES = HEADS * TC_W2_HEAD_BYTES;
   static_assert(A2_BYTES + W2_BYTES <= STAGES * STAGE_BYTES, "layer-2 operands reuse the drained ring");
   static constexpr int BAR_BYTES = 256;
-  static constexpr int CONST_FLOATS = 2 * TC_COLS + 4 * HD_HS + 8;           // b1 | b2 | w3 | b3 | logstd
+  static constexpr int CONST_FLOATS = 2 * TC_COLS + 4 * HD_HS + 8 + 4 * TC_M;   // b1 | b2 | w3 | b3 | partial outputs of the upper column half
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + BAR_BYTES + CONST_FLOATS * 4;
 };
 
@@ -97,21 +100,32 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), leading
 // byte offset (unused for swizzled K-major layouts; 1) in [16,30), stride byte offset = 1024 B (next 8-row atom) >> 4 in
-// [32,46), descriptor version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64)
-__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
+// [32,46), descriptor version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64): low word = tc_desc_lo(address), high word constant
 // instruction descriptor (cute::UMMA::InstrDescriptor), kind::tf32: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
 // N >> 3 in [17,23), M >> 4 in [24,29)
 template <int NT>
 __host__ __device__ constexpr uint32_t tc_idesc() { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24); }
 
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// low word of the descriptor above (start address | leading byte offset); the high word is the constant TC_DESC_HI
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+
+// one MMA: D[tmem] (+)= A[desc a] * B[desc b]; descriptors passed as their low words (advancing along K = + 2 per UMMA_K step)
+template <bool ACC>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %4};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(TC_DESC_HI), "r"(ACC ? 1u : 0u)
       : "memory");
+}
+// one elected lane of a converged warp (elect.sync): the compiler keeps the enclosed code on the uniform datapath
+__device__ __forceinline__ bool tc_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {  // implies tcgen05.fence::before_thread_sync
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
@@ -142,25 +156,25 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
   using SH = TCShape<NT, ST, AH>;
   constexpr int STAGES = SH::STAGES, HEADS = SH::HEADS, TC_AHEAD = SH::AHEAD;
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024-byte aligned
+  uint8_t* smem = tc_smem_raw + ((1024u - (tc_smem_u32(tc_smem_raw) & 1023u)) & 1023u);  // swizzle atoms: 1024-byte aligned (offset, so the pointer stays a shared-memory one)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * SH::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* accum = empty + STAGES;      // accum[0]: layer-1 accumulators complete, accum[1]: layer-2 accumulators complete
   uint64_t* full2 = accum + 2;           // layer-2 operands (H1 tiles + weight tiles) in place
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full2 + 1);
   float* cst = reinterpret_cast<float*>(smem + STAGES * SH::STAGE_BYTES + SH::BAR_BYTES);
-  float* b1s = cst, *b2s = cst + TC_COLS, *w3s = cst + 2 * TC_COLS, *b3s = w3s + 4 * HD_HS;
+  float* b1s = cst, *b2s = cst + TC_COLS, *w3s = cst + 2 * TC_COLS, *b3s = w3s + 4 * HD_HS, *opart = b3s + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int e0 = blockIdx.x * TC_M;
   const int ny = TC_COLS / NT, y = blockIdx.y;   // NT = 64: y = 0 critic, y = 1 actor
   const HArgs& h = a.h;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { tc_mbar_init(&full[s], 128); tc_mbar_init(&empty[s], 1); }
-    tc_mbar_init(&accum[0], 1); tc_mbar_init(&accum[1], 1); tc_mbar_init(full2, 128);
+    for (int s = 0; s < STAGES; ++s) { tc_mbar_init(&full[s], TC_ET); tc_mbar_init(&empty[s], 1); }
+    tc_mbar_init(&accum[0], 1); tc_mbar_init(&accum[1], 1); tc_mbar_init(full2, TC_ET);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {  // 2 NT TMEM columns of float32 accumulators (layer 1 | layer 2), one warp allocates and later frees
+  if (warp == TC_EW) {  // 2 NT TMEM columns of float32 accumulators (layer 1 | layer 2), one warp allocates and later frees
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "n"(2 * NT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -174,48 +188,53 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
   uint8_t* a2 = smem;                       // H1 operand tiles: k-chunk j at j * 32 KB (hi | lo)
   uint8_t* w2 = smem + SH::A2_BYTES;        // layer-2 weight tiles of this CTA's head(s)
 
-  if (warp == 4) {
-    if (lane == 0) {
-      // ---- layer 1: 12 tcgen05.mma per chunk, stage handed back through tcgen05.commit
-      constexpr uint32_t IDESC1 = tc_idesc<NT>(), IDESC2 = tc_idesc<HD_HS>();
-      for (int c = 0; c < a.chunks; ++c) {
-        const int s = c % STAGES;
-        tc_mbar_wait(&full[s], (uint32_t)((c / STAGES) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t base = tc_smem_u32(smem + s * SH::STAGE_BYTES);
+  if (warp == TC_EW) {
+    // ---- MMA issue: the whole warp follows the barriers, ONE elected lane issues (12 tcgen05.mma per chunk, stage handed back
+    // through tcgen05.commit)
+    constexpr uint32_t IDESC1 = tc_idesc<NT>(), IDESC2 = tc_idesc<HD_HS>();
+    for (int c = 0; c < a.chunks; ++c) {
+      const int s = c % STAGES;
+      tc_mbar_wait(&full[s], (uint32_t)((c / STAGES) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tc_elect()) {
+        const uint32_t xh = tc_desc_lo(tc_smem_u32(smem + s * SH::STAGE_BYTES)), xl = xh + (TC_XTILE_BYTES >> 4);
+        const uint32_t wh = xh + (2 * TC_XTILE_BYTES >> 4), wl = wh + (SH::WTILE_BYTES >> 4);
+        if (c == 0) tc_mma<false>(tmem, xh, wh, IDESC1); else tc_mma<true>(tmem, xh, wh, IDESC1);
+        tc_mma<true>(tmem, xl, wh, IDESC1);
+        tc_mma<true>(tmem, xh, wl, IDESC1);
 #pragma unroll
-        for (int k = 0; k < TC_KC / 8; ++k) {  // UMMA_K = 8 float32 = 32 bytes along the swizzled row
-          const uint64_t xh = tc_desc(base + k * 32), xl = tc_desc(base + TC_XTILE_BYTES + k * 32);
-          const uint64_t wh = tc_desc(base + 2 * TC_XTILE_BYTES + k * 32), wl = tc_desc(base + 2 * TC_XTILE_BYTES + SH::WTILE_BYTES + k * 32);
-          tc_mma(tmem, xh, wh, IDESC1, (c > 0 || k > 0) ? 1u : 0u);
-          tc_mma(tmem, xl, wh, IDESC1, 1u);
-          tc_mma(tmem, xh, wl, IDESC1, 1u);
+        for (int k = 1; k < TC_KC / 8; ++k) {  // UMMA_K = 8 float32 = 32 bytes along the swizzled row = + 2 in the descriptor
+          tc_mma<true>(tmem, xh + 2 * k, wh + 2 * k, IDESC1);
+          tc_mma<true>(tmem, xl + 2 * k, wh + 2 * k, IDESC1);
+          tc_mma<true>(tmem, xh + 2 * k, wl + 2 * k, IDESC1);
         }
         tc_commit(&empty[s]);
+        if (c == a.chunks - 1) tc_commit(&accum[0]);
       }
-      tc_commit(&accum[0]);
-      // ---- layer 2: per head [128 x 64] x [64 x 64], operands written by epilogue 1 / the second bulk copy
-      tc_mbar_wait(full2, 0u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      __syncwarp();
+    }
+    // ---- layer 2: per head [128 x 64] x [64 x 64], operands written by epilogue 1 / the second bulk copy
+    tc_mbar_wait(full2, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tc_elect()) {
 #pragma unroll
       for (int hd = 0; hd < HEADS; ++hd) {
+        const uint32_t d = tmem + (uint32_t)(NT + hd * HD_HS);
 #pragma unroll
         for (int c = 0; c < HD_HS / TC_KC; ++c) {
-          const uint32_t ab = tc_smem_u32(a2 + (hd * (HD_HS / TC_KC) + c) * 2 * TC_XTILE_BYTES);
-          const uint32_t wb = tc_smem_u32(w2 + hd * TC_W2_HEAD_BYTES + c * (2 * HD_HS * TC_KC * 4));
+          const uint32_t xh = tc_desc_lo(tc_smem_u32(a2 + (hd * (HD_HS / TC_KC) + c) * 2 * TC_XTILE_BYTES)), xl = xh + (TC_XTILE_BYTES >> 4);
+          const uint32_t wh = tc_desc_lo(tc_smem_u32(w2 + hd * TC_W2_HEAD_BYTES + c * (2 * HD_HS * TC_KC * 4))), wl = wh + (HD_HS * TC_KC * 4 >> 4);
 #pragma unroll
           for (int k = 0; k < TC_KC / 8; ++k) {
-            const uint64_t xh = tc_desc(ab + k * 32), xl = tc_desc(ab + TC_XTILE_BYTES + k * 32);
-            const uint64_t wh = tc_desc(wb + k * 32), wl = tc_desc(wb + HD_HS * TC_KC * 4 + k * 32);
-            const uint32_t d = tmem + (uint32_t)(NT + hd * HD_HS);
-            tc_mma(d, xh, wh, IDESC2, (c > 0 || k > 0) ? 1u : 0u);
-            tc_mma(d, xl, wh, IDESC2, 1u);
-            tc_mma(d, xh, wl, IDESC2, 1u);
+            if (c == 0 && k == 0) tc_mma<false>(d, xh, wh, IDESC2); else tc_mma<true>(d, xh + 2 * k, wh + 2 * k, IDESC2);
+            tc_mma<true>(d, xl + 2 * k, wh + 2 * k, IDESC2);
+            tc_mma<true>(d, xh + 2 * k, wl + 2 * k, IDESC2);
           }
         }
       }
       tc_commit(&accum[1]);
     }
+    __syncwarp();
   } else {
     // ---- producers.  X travels global -> shared as raw float32 straight into the swizzled "hi" tile (cp.async, 16 bytes per
     // request, TC_AHEAD chunks ahead): kind::tf32 ignores the 13 low mantissa bits of its operands, so the raw value IS
@@ -227,8 +246,8 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
       if (use > 0) tc_mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));  // the MMAs that read this stage have completed
       uint8_t* st = smem + s * SH::STAGE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = i * 128 + tid, r = idx >> 3, c4 = idx & 7;
+      for (int i = 0; i < 1024 / TC_ET; ++i) {
+        const int idx = i * TC_ET + tid, r = idx >> 3, c4 = idx & 7;
         const int e = e0 + r, q = c * 8 + c4;
         const bool in = e < h.E && q < kq;
         cp_async16(reinterpret_cast<float*>(st + tc_swizzle(r, c4)), h.emb + (in ? (size_t)e * h.K + 4 * q : (size_t)0), in ? 16 : 0);
@@ -249,8 +268,8 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
       cp_async_wait<TC_AHEAD>();       // this thread's requests of chunk c have landed
       uint8_t* st = smem + (c % STAGES) * SH::STAGE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = i * 128 + tid, r = idx >> 3, c4 = idx & 7;
+      for (int i = 0; i < 1024 / TC_ET; ++i) {
+        const int idx = i * TC_ET + tid, r = idx >> 3, c4 = idx & 7;
         const uint32_t off = tc_swizzle(r, c4);
         const float4 x = *reinterpret_cast<const float4*>(st + off);
         *reinterpret_cast<float4*>(st + TC_XTILE_BYTES + off) =
@@ -266,9 +285,13 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
       tc_mbar_expect_tx(full2, SH::W2_BYTES);
       tc_bulk_load(w2, a.w2tc + (size_t)(NT == 64 ? y : 0) * (TC_W2_HEAD_BYTES / 4), SH::W2_BYTES, full2);
     }
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // warp w: TMEM lane quarter w & 3 (the hardware's rule: a warp reads lanes 32 (w % 4) ..), column half w >> 2 of the CTA's NT
+    const int row = (warp & 3) * 32 + lane, ch = warp >> 2;
+    constexpr int CW = NT / (TC_EW / 4);                        // columns per warp
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
-    for (int j = 0; j < NT / 32; ++j) {
+    for (int jj = 0; jj < CW / 32; ++jj) {
+      const int j = ch * (CW / 32) + jj;                        // 32-column block = k-chunk of layer 2
       uint32_t v[32];
       tc_tmem_ld32(trow + (uint32_t)(j * 32), v);
       uint8_t* tile = a2 + j * 2 * TC_XTILE_BYTES;
@@ -282,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
         hi.y = tc_hi(t.y); lo.y = t.y - hi.y;
         hi.z = tc_hi(t.z); lo.z = t.z - hi.z;
         hi.w = tc_hi(t.w); lo.w = t.w - hi.w;
-        const uint32_t off = tc_swizzle(tid, i >> 2);
+        const uint32_t off = tc_swizzle(row, i >> 2);
         *reinterpret_cast<float4*>(tile + off) = hi;
         *reinterpret_cast<float4*>(tile + TC_XTILE_BYTES + off) = lo;
       }
@@ -292,9 +315,10 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
     // ---- epilogue 2: H2 = tanh(. + b2) and the output layer as dot products over the TMEM loads, then the sampling tail
     tc_mbar_wait(&accum[1], 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float o[4] = {b3s[0], b3s[1], b3s[2], b3s[3]};
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int j = 0; j < NT / 32; ++j) {
+    for (int jj = 0; jj < CW / 32; ++jj) {
+      const int j = ch * (CW / 32) + jj;
       uint32_t v[32];
       tc_tmem_ld32(trow + (uint32_t)(NT + j * 32), v);
       const int col0 = y * NT + j * 32;               // hidden column of v[0]: < 64 critic, >= 64 actor
@@ -312,12 +336,24 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
         }
       }
     }
-    const int e = e0 + tid;
-    if (e < h.E) heads_finish(h, e, o, NT == 128 || y == 0, NT == 128 || y == 1);
+    const int e = e0 + row;
+    if constexpr (NT == 128) {   // column half 0 = the critic's 64 columns, half 1 = the actor's: every thread finishes one head
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[c] += b3s[c];
+      if (e < h.E) heads_finish(h, e, o, ch == 0, ch == 1);
+    } else {                     // the head's 64 columns are split over the two halves: the upper half hands its partial sums over
+      if (ch == 1) *reinterpret_cast<float4*>(opart + 4 * row) = make_float4(o[0], o[1], o[2], o[3]);
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_ET) : "memory");
+      if (ch == 0) {
+        const float4 u = *reinterpret_cast<const float4*>(opart + 4 * row);
+        o[0] = b3s[0] + (o[0] + u.x); o[1] = b3s[1] + (o[1] + u.y); o[2] = b3s[2] + (o[2] + u.z); o[3] = b3s[3] + (o[3] + u.w);
+        if (e < h.E) heads_finish(h, e, o, y == 0, y == 1);
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_EW) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NT) : "memory");
   }

@@ -292,7 +292,10 @@ typedef struct EvacPolicyIO {
   int64_t env_index_offset;  /* global index of env 0 (sharding-invariant streams, like evac_create) */
 } EvacPolicyIO;
 
-/* embedding kernel (+ heads kernel if any head output is requested), asynchronous on `stream` */
+/* embedding kernel (+ heads kernel if any head output is requested), asynchronous on `stream`.  The heads -- the 372 x 128 and
+ * 64 x 64 dense layers of rpo_linear_agent_network.py:23-42, the one dense contraction on this path -- run as 3xTF32 tcgen05.mma with
+ * the accumulators in tensor memory (csrc/evac_policy_tc.cuh) whenever S * D is a multiple of 4; otherwise, or with EVAC_POLICY_TC=0 in
+ * the environment at evac_policy_create, on the CUDA cores.  Both agree with a float64 evaluation to 3e-6. */
 int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream);
 int64_t evac_policy_launch_count(const EvacPolicy* p);
 

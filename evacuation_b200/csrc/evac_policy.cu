@@ -360,6 +360,14 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
     if (!wide) { t.w1tc = p->d_w1tc64; k64<<<dim3(gx, 2), TC_THREADS, S64::SMEM_BYTES, st>>>(t); }
     else { t.w1tc = p->d_w1tc128; k128<<<dim3(gx, 1), TC_THREADS, S128::SMEM_BYTES, st>>>(t); }
     PCK(cudaGetLastError());
+#ifdef EVAC_TC_TRACE
+    if (getenv("EVAC_TC_TRACE_PRINT")) {
+      unsigned long long tr[2][16];
+      cudaDeviceSynchronize();
+      cudaMemcpyFromSymbol(tr, tc_trace, sizeof(tr));
+      for (int w = 0; w < 2; ++w) { fprintf(stderr, "tc_trace %s:", w ? "mma" : "producer"); for (int i = 1; i < 10; ++i) fprintf(stderr, " %lld", tr[w][i] ? (long long)(tr[w][i] - tr[0][0]) : -1LL); fprintf(stderr, "\n"); }
+    }
+#endif
     p->launches++;
     return EVAC_OK;
   }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -309,6 +310,8 @@ int evac_policy_forward(EvacPolicy* p, const EvacPolicyIO* io, void* stream) {
     if (rc) return rc;
   }
   if (!emb) emb = p->d_scratch;
+  if ((p->K & 3) == 0 && (reinterpret_cast<uintptr_t>(emb) & 15u) != 0)  // the heads read the rows with 16-byte requests
+    return pfail(EVAC_ERR_INVALID, "embedding buffer must be 16-byte aligned");
   const bool train = io->training != 0 && p->cfg.dropout > 0.f;
   PArgs a;
   memset(&a, 0, sizeof(a));

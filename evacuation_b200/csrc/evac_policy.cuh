@@ -164,11 +164,15 @@ __device__ __noinline__ void attn_row_exact(const float* __restrict__ ks, const 
   for (int h = 0; h < H; ++h) out[h] = acc[h] / l;
 }
 
-// four keys j .. j+3 against the two query rows of this lane
+// four keys j .. j+3 against the two query rows (a, b) of this lane.  Scores are packed over key PAIRS (query as the
+// scalar-broadcast operand); the probabilities, the normaliser and the probability-weighted value sums are packed over the
+// two ROWS: acc[h] = (row a, row b) += (p_a, p_b) * v_j[h] with the value as the 32-bit broadcast operand and (p_a, p_b)
+// shared by the H consecutive instructions of a key -- the FMA pipe's full-rate operand forms (three distinct
+// 64-bit sources run at 61 %), and the sums run over the keys in index order.
 template <int H, bool TAIL>
 __device__ __forceinline__ void attn_group(const float* __restrict__ ks, const float* __restrict__ vs, int j, int nvalid,
                                            const float2 (&qa)[H], const float2 (&qb)[H], float2 nma, float2 nmb,
-                                           float2& la, float2& lb, float2 (&acca)[H], float2 (&accb)[H]) {
+                                           float2& l, float2 (&acc)[H]) {
   float4 k4[H], v4[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) {
@@ -184,19 +188,17 @@ __device__ __forceinline__ void attn_group(const float* __restrict__ ks, const f
       sa = __ffma2_rn(qa[h], kk, sa);
       sb = __ffma2_rn(qb[h], kk, sb);
     }
-    float2 pa = make_float2(ex2(sa.x), ex2(sa.y)), pb = make_float2(ex2(sb.x), ex2(sb.y));
+    float2 p0 = make_float2(ex2(sa.x), ex2(sb.x)), p1 = make_float2(ex2(sa.y), ex2(sb.y));  // key 2 half, key 2 half + 1: (row a, row b)
     if (TAIL) {
-      if (2 * half >= nvalid) { pa.x = 0.f; pb.x = 0.f; }
-      if (2 * half + 1 >= nvalid) { pa.y = 0.f; pb.y = 0.f; }
+      if (2 * half >= nvalid) p0 = make_float2(0.f, 0.f);
+      if (2 * half + 1 >= nvalid) p1 = make_float2(0.f, 0.f);
     }
-    la = __fadd2_rn(la, pa);
-    lb = __fadd2_rn(lb, pb);
+    l = __fadd2_rn(l, p0);
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
-      const float2 vv = half ? hi(v4[h]) : lo(v4[h]);
-      acca[h] = __ffma2_rn(pa, vv, acca[h]);
-      accb[h] = __ffma2_rn(pb, vv, accb[h]);
-    }
+    for (int h = 0; h < H; ++h) acc[h] = __ffma2_rn(p0, splat(half ? v4[h].z : v4[h].x), acc[h]);
+    l = __fadd2_rn(l, p1);
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] = __ffma2_rn(p1, splat(half ? v4[h].w : v4[h].y), acc[h]);
   }
 }
 
@@ -318,21 +320,21 @@ __global__ void __launch_bounds__(PW_WARPS * 32, EVAC_PW_MINB) evac_policy_embed
       const float kn = fmaxf(va ? kn_a : 0.f, vb ? kn_b : 0.f);
       const float kmax = sqrtf(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(kn))));
       const float2 nma = splat(-sqrtf(qn_a) * kmax), nmb = splat(-sqrtf(qn_b) * kmax);
-      float2 qa2[H], qb2[H], acca[H], accb[H];
+      float2 qa2[H], qb2[H], acc[H];   // acc[h] = (row a, row b)
 #pragma unroll
-      for (int h = 0; h < H; ++h) { qa2[h] = splat(qa[h]); qb2[h] = splat(qb[h]); acca[h] = accb[h] = make_float2(0.f, 0.f); }
-      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+      for (int h = 0; h < H; ++h) { qa2[h] = splat(qa[h]); qb2[h] = splat(qb[h]); acc[h] = make_float2(0.f, 0.f); }
+      float2 l = make_float2(0.f, 0.f);
       __syncwarp();
       int j = 0;
 #pragma unroll 2
-      for (; j + 4 <= S; j += 4) attn_group<H, false>(ks, vs, j, 4, qa2, qb2, nma, nmb, la, lb, acca, accb);
-      if (j < S) attn_group<H, true>(ks, vs, j, S - j, qa2, qb2, nma, nmb, la, lb, acca, accb);
+      for (; j + 4 <= S; j += 4) attn_group<H, false>(ks, vs, j, 4, qa2, qb2, nma, nmb, l, acc);
+      if (j < S) attn_group<H, true>(ks, vs, j, S - j, qa2, qb2, nma, nmb, l, acc);
       float oa[H], ob[H];
-      const float sum_a = la.x + la.y, sum_b = lb.x + lb.y;
+      const float sum_a = l.x, sum_b = l.y;
       {
         const float ia = 1.f / sum_a, ib = 1.f / sum_b;
 #pragma unroll
-        for (int h = 0; h < H; ++h) { oa[h] = (acca[h].x + acca[h].y) * ia; ob[h] = (accb[h].x + accb[h].y) * ib; }
+        for (int h = 0; h < H; ++h) { oa[h] = acc[h].x * ia; ob[h] = acc[h].y * ib; }
       }
       // a bound so loose that every term underflowed (or a non-finite input): redo the row with the exact maximum
       const bool bad_a = va && !(sum_a >= 1e-30f && sum_a <= 3e38f), bad_b = vb && !(sum_b >= 1e-30f && sum_b <= 3e38f);

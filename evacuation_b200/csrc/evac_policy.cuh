@@ -211,6 +211,16 @@ __global__ void __launch_bounds__(PW_WARPS * 32, EVAC_PW_MINB) evac_policy_embed
     const int n4 = a.NB * a.wstride / 4;
     const float4* __restrict__ src = reinterpret_cast<const float4*>(a.w);
     for (int i = threadIdx.x; i < n4; i += blockDim.x) smem4[i] = src[i];
+    if (TRAIN) {
+      // dropout of the hidden layer: relu(m s h) W2 = relu(m h) (s W2) for s = 1 / (1 - p) > 0 -- the scale is folded into the
+      // staged copy of W2, the mask only zeroes
+      __syncthreads();
+      const int groups = a.F4 >> 2;
+      for (int i = threadIdx.x; i < a.NB * groups * 4 * D; i += blockDim.x) {
+        const int b = i / (groups * 4 * D), r = i - b * (groups * 4 * D), g = r / (4 * D), t = r - g * (4 * D);
+        wsm[b * a.wstride + L::FF + g * L::GS + 4 + 4 * D + t] *= a.drop_scale;
+      }
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -377,13 +387,21 @@ __global__ void __launch_bounds__(PW_WARPS * 32, EVAC_PW_MINB) evac_policy_embed
         h01b = __ffma2_rn(xsb[c], lo(w), h01b); h23b = __ffma2_rn(xsb[c], hi(w), h23b);
       }
       if (TRAIN) {
+        // four 16-bit words per row: the two halves of one fmix32 word and of a cheap second mix of it (multiply + xor-shift);
+        // a word below the threshold drops the element (the 1 / (1 - p) scale sits in the staged W2, see above).  The upper
+        // halves are compared in place against the threshold shifted up.
         const uint32_t ta = fmix32(key_a + (8u + g) * 0x9E3779B9u), tb = fmix32(key_b + (8u + g) * 0x9E3779B9u);
-        const uint32_t ta2 = fmix32(ta + 0x7F4A7C15u), tb2 = fmix32(tb + 0x7F4A7C15u);
-        const float s = a.drop_scale;
-        h01a.x *= (ta & 0xFFFFu) < a.drop_thresh ? 0.f : s; h01a.y *= (ta >> 16) < a.drop_thresh ? 0.f : s;
-        h23a.x *= (ta2 & 0xFFFFu) < a.drop_thresh ? 0.f : s; h23a.y *= (ta2 >> 16) < a.drop_thresh ? 0.f : s;
-        h01b.x *= (tb & 0xFFFFu) < a.drop_thresh ? 0.f : s; h01b.y *= (tb >> 16) < a.drop_thresh ? 0.f : s;
-        h23b.x *= (tb2 & 0xFFFFu) < a.drop_thresh ? 0.f : s; h23b.y *= (tb2 >> 16) < a.drop_thresh ? 0.f : s;
+        uint32_t ta2 = ta * 0x9E3779B1u, tb2 = tb * 0x9E3779B1u;
+        ta2 ^= ta2 >> 15; tb2 ^= tb2 >> 15;
+        const uint32_t th = a.drop_thresh << 16;
+        if ((ta << 16) < th) h01a.x = 0.f;
+        if (ta < th) h01a.y = 0.f;
+        if ((ta2 << 16) < th) h23a.x = 0.f;
+        if (ta2 < th) h23a.y = 0.f;
+        if ((tb << 16) < th) h01b.x = 0.f;
+        if (tb < th) h01b.y = 0.f;
+        if ((tb2 << 16) < th) h23b.x = 0.f;
+        if (tb2 < th) h23b.y = 0.f;
       }
       h01a.x = max_nan(h01a.x, 0.f); h01a.y = max_nan(h01a.y, 0.f); h23a.x = max_nan(h23a.x, 0.f); h23a.y = max_nan(h23a.y, 0.f);
       h01b.x = max_nan(h01b.x, 0.f); h01b.y = max_nan(h01b.y, 0.f); h23b.x = max_nan(h23b.x, 0.f); h23b.y = max_nan(h23b.y, 0.f);

@@ -86,7 +86,11 @@ __device__ __forceinline__ float2 hi(const float4& v) { return make_float2(v.z, 
 // NaN-propagating max / min (torch.relu / torch.clamp keep NaN; fmaxf / fminf would drop it)
 __device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float min_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+#ifdef EVAC_PROBE_NOEXP  // measurement variant (never shipped): the attention loop without its MUFU.EX2
+__device__ __forceinline__ float ex2(float x) { return x * 0.001f + 1.f; }
+#else
 __device__ __forceinline__ float ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 
 __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
@@ -194,11 +198,15 @@ __device__ __forceinline__ void attn_group(const float* __restrict__ ks, const f
       if (2 * half + 1 >= nvalid) p1 = make_float2(0.f, 0.f);
     }
     l = __fadd2_rn(l, p0);
+    l = __fadd2_rn(l, p1);
+#ifndef EVAC_PROBE_NOVAL  // (measurement variant, never shipped: the attention loop without its value FFMA2s)
 #pragma unroll
     for (int h = 0; h < H; ++h) acc[h] = __ffma2_rn(p0, splat(half ? v4[h].z : v4[h].x), acc[h]);
-    l = __fadd2_rn(l, p1);
 #pragma unroll
     for (int h = 0; h < H; ++h) acc[h] = __ffma2_rn(p1, splat(half ? v4[h].w : v4[h].y), acc[h]);
+#else
+    acc[0] = __fadd2_rn(acc[0], lo(v4[half]));
+#endif
   }
 }
 

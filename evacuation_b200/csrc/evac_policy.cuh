@@ -180,8 +180,16 @@ __device__ __forceinline__ void attn_group(const float* __restrict__ ks, const f
   float4 k4[H], v4[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) {
+#ifdef EVAC_PROBE_NOLDS  // measurement variant (never shipped): opaque register moves instead of the six broadcast LDS.128
+    {
+      auto opq = [](float y) { float x; asm volatile("mov.f32 %0, %1;" : "=f"(x) : "f"(y)); return x; };
+      k4[h] = make_float4(opq(qa[h].x), opq(qb[h].x), opq(nma.x), opq(nmb.x));
+      v4[h] = make_float4(opq(qb[h].x), opq(qa[h].x), opq(nmb.x), opq(nma.x));
+    }
+#else
     k4[h] = *reinterpret_cast<const float4*>(ks + h * PW_MAX_S + j);
     v4[h] = *reinterpret_cast<const float4*>(vs + h * PW_MAX_S + j);
+#endif
   }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {

@@ -908,9 +908,13 @@ int evac_probe_pairwise(int32_t device, int32_t num_envs, int32_t n, int32_t rep
   const size_t tb = Tile<float>::bytes(64);
   for (int rep = 0; rep < 2; ++rep) {
     CK(cudaEventRecord(e0));
-    const char* hw = getenv("EVAC_PROBE_HALFWARP");  // A/B: 16 lanes x 4 pedestrians per environment, two environments per warp (unroll 1 | 2 | 4)
+    const char* hw = getenv("EVAC_PROBE_HALFWARP");  // A/B: 16 lanes x 4 pedestrians per environment, two environments per warp (unroll 1 | 2 | 4); 8: 8 lanes x 8
     if (hw && atoi(hw) == 1) probe_pairwise_kernel<16, 4, 1, 2, 16><<<(num_envs + 1) / 2, 32, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
     else if (hw && atoi(hw) == 2) probe_pairwise_kernel<16, 4, 2, 2, 16><<<(num_envs + 1) / 2, 32, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
+    // quarter warp x 8 pedestrians per environment, four environments per warp: one broadcast LDS.128 pair per 64 packed math
+    // instructions (32 x 2: per 16) -- measured 50.9 % of the FFMA2 peak at 65 536 x 60 (32 x 2: 46.2 %, 16 x 4: 48.1 %); unroll 1 / 4,
+    // 12 resident warps or eight environments per CTA: 46.4 / 48.3 / 50.1 / 50.2 %
+    else if (hw && atoi(hw) == 8) probe_pairwise_kernel<8, 8, 2, 4, 16><<<(num_envs + 3) / 4, 32, 4 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
     else if (hw && atoi(hw) == 4) probe_pairwise_kernel<16, 4, 4, 2, 16><<<(num_envs + 1) / 2, 32, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
     else if (shape_32x2 && wpc == 2) probe_pairwise_kernel<32, 2, 4, 2, 20><<<(num_envs + 1) / 2, 64, 2 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);
     else if (shape_32x2 && wpc == 4) probe_pairwise_kernel<32, 2, 4, 4, 10><<<(num_envs + 3) / 4, 128, 4 * tb>>>(pos, unit, out, n, reps, thr2, num_envs);

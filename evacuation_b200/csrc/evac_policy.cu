@@ -47,7 +47,6 @@ struct EvacPolicy {
   float *d_w1tc64 = nullptr, *d_w1tc128 = nullptr, *d_w2tc = nullptr;
   int tc_chunks = 0;
   bool use_tc = false;
-  int embed_rows = 1;          // row pairs per lane of the embedding kernel: 1 = one warp per environment, 2 = half a warp (EVAC_POLICY_EMBED=warp | half)
   bool loaded = false;
   int64_t launches = 0;
   size_t embed_smem = 0, heads_smem = 0;
@@ -103,23 +102,6 @@ static void pack_block(const float* src, float* dst, int F, int F4) {
 
 template <int D, int H>
 static int launch_embed(EvacPolicy* p, const PArgs& a, bool train, cudaStream_t st) {
-  if (p->embed_rows == 2) {  // half a warp per environment (evac_policy_embed_rows_kernel<.., P = 2>)
-    auto k_eval = evac_policy_embed_rows_kernel<D, H, false, 2>;
-    auto k_train = evac_policy_embed_rows_kernel<D, H, true, 2>;
-    const size_t smem = ((size_t)p->NB * p->wstride + (size_t)PW_WARPS * 2 * 2 * p->H * PW_MAX_S) * sizeof(float);
-    static thread_local size_t attr_set2[16] = {0};
-    if (smem > 48 * 1024 && attr_set2[p->device & 15] < smem) {
-      PCK(cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PCK(cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set2[p->device & 15] = smem;
-    }
-    const int grid = (a.E + 2 * PW_WARPS - 1) / (2 * PW_WARPS);
-    if (train) k_train<<<grid, PW_WARPS * 32, smem, st>>>(a);
-    else k_eval<<<grid, PW_WARPS * 32, smem, st>>>(a);
-    PCK(cudaGetLastError());
-    p->launches++;
-    return EVAC_OK;
-  }
   auto k_eval = evac_policy_embed_kernel<D, H, false>;
   auto k_train = evac_policy_embed_kernel<D, H, true>;
   static thread_local size_t attr_set[16] = {0};
@@ -186,7 +168,6 @@ int evac_policy_create(const EvacPolicyConfig* cfg, int32_t device, EvacPolicy**
   alloc(&p->d_w1t, (size_t)p->K16 * HD_COLS); alloc(&p->d_b1, HD_COLS);
   alloc(&p->d_w2t, (size_t)HD_HS * HD_COLS); alloc(&p->d_b2, HD_COLS);
   alloc(&p->d_w3, (size_t)(1 + p->A) * HD_HS); alloc(&p->d_b3, 4); alloc(&p->d_logstd, 4);
-  { const char* er = getenv("EVAC_POLICY_EMBED"); p->embed_rows = (er && strcmp(er, "half") == 0 && p->S <= 64) ? 2 : 1; }
   // EVAC_POLICY_TC=0 keeps layer 1 of the heads on the CUDA cores (A/B switch); the tensor-core kernel reads float4 rows (K % 4 == 0)
   const char* tc_env = getenv("EVAC_POLICY_TC");
   p->use_tc = (p->K % 4 == 0) && !(tc_env && tc_env[0] == '0');

@@ -443,309 +443,6 @@ __global__ void __launch_bounds__(PW_WARPS * 32, EVAC_PW_MINB) evac_policy_embed
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// The same embedding with P row PAIRS per lane and 32 / P lanes per environment (P = 2: half a warp per environment, lane l owns
-// rows l, l + 16, l + 32, l + 48; two environments per warp).  Every broadcast LDS.128 -- the keys and values of the attention
-// loop, the weights of the projections and of the feed-forward -- then serves 2 P rows instead of 2: the shared-memory pipe is
-// the co-limiter of evac_policy_embed_kernel (-26 % without the attention loop's loads, profiles/r02y/embed_phase_probes.txt).
-// Arithmetic, summation order and dropout streams per row are those of evac_policy_embed_kernel: the outputs are bit-identical.
-#ifndef EVAC_PWR_MINB
-#define EVAC_PWR_MINB 2
-#endif
-#ifndef EVAC_PWR_UNROLL
-#define EVAC_PWR_UNROLL 1
-#endif
-template <int H, int P, bool TAIL>
-__device__ __forceinline__ void attn_group_rows(const float* __restrict__ ks, const float* __restrict__ vs, int j, int nvalid,
-                                                const float2 (&q2)[2 * P][H], const float2 (&nm)[2 * P], float2 (&l)[P], float2 (&acc)[P][H]) {
-  float4 k4[H], v4[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) {
-    k4[h] = *reinterpret_cast<const float4*>(ks + h * PW_MAX_S + j);
-    v4[h] = *reinterpret_cast<const float4*>(vs + h * PW_MAX_S + j);
-  }
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float2 sa = nm[2 * p], sb = nm[2 * p + 1];
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float2 kk = half ? hi(k4[h]) : lo(k4[h]);
-        sa = __ffma2_rn(q2[2 * p][h], kk, sa);
-        sb = __ffma2_rn(q2[2 * p + 1][h], kk, sb);
-      }
-      float2 p0 = make_float2(ex2(sa.x), ex2(sb.x)), p1 = make_float2(ex2(sa.y), ex2(sb.y));
-      if (TAIL) {
-        if (2 * half >= nvalid) p0 = make_float2(0.f, 0.f);
-        if (2 * half + 1 >= nvalid) p1 = make_float2(0.f, 0.f);
-      }
-      l[p] = __fadd2_rn(l[p], p0);
-#pragma unroll
-      for (int h = 0; h < H; ++h) acc[p][h] = __ffma2_rn(p0, splat(half ? v4[h].z : v4[h].x), acc[p][h]);
-      l[p] = __fadd2_rn(l[p], p1);
-#pragma unroll
-      for (int h = 0; h < H; ++h) acc[p][h] = __ffma2_rn(p1, splat(half ? v4[h].w : v4[h].y), acc[p][h]);
-    }
-  }
-}
-
-template <int D, int H, bool TRAIN, int P>
-__global__ void __launch_bounds__(PW_WARPS * 32, EVAC_PWR_MINB) evac_policy_embed_rows_kernel(const __grid_constant__ PArgs a) {
-  using L = EmbLayout<D, H>;
-  constexpr int LW = 32 / P, R = 2 * P;
-  extern __shared__ float4 smem4[];
-  float* wsm = reinterpret_cast<float*>(smem4);
-  {  // packed weights: once per CTA (training: the dropout scale folded into W2, see evac_policy_embed_kernel)
-    const int n4 = a.NB * a.wstride / 4;
-    const float4* __restrict__ src = reinterpret_cast<const float4*>(a.w);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) smem4[i] = src[i];
-    if (TRAIN) {
-      __syncthreads();
-      const int groups = a.F4 >> 2;
-      for (int i = threadIdx.x; i < a.NB * groups * 4 * D; i += blockDim.x) {
-        const int b = i / (groups * 4 * D), r = i - b * (groups * 4 * D), g = r / (4 * D), t = r - g * (4 * D);
-        wsm[b * a.wstride + L::FF + g * L::GS + 4 + 4 * D + t] *= a.drop_scale;
-      }
-    }
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sub = lane / LW, hl = lane % LW;
-  const int e = (blockIdx.x * PW_WARPS + warp) * P + sub;
-  if (e >= a.E) return;  // every collective below names the lanes of its own environment only
-  const uint32_t hm = P == 1 ? 0xffffffffu : (((1u << LW) - 1u) << (LW * sub));
-  float* ks = wsm + a.NB * a.wstride + (warp * P + sub) * (2 * H * PW_MAX_S);
-  float* vs = ks + H * PW_MAX_S;
-  const int S = a.S;
-  int row[R];
-  bool val[R];
-#pragma unroll
-  for (int k = 0; k < R; ++k) { row[k] = hl + k * LW; val[k] = row[k] < S; }
-  const size_t row0 = (size_t)e * S * D;
-
-  float x[R][D];
-#pragma unroll
-  for (int k = 0; k < R; ++k) {
-#pragma unroll
-    for (int c = 0; c < D; ++c) x[k][c] = 0.f;
-    if (val[k]) load_row<D>(a.obs + row0 + row[k] * D, x[k]);
-  }
-  if (a.norm_mean != nullptr) {
-    const double cnt = *a.norm_count, tot = cnt + 1.0;
-    const float w_new = (float)(1.0 / tot), w_old = (float)(cnt / tot);
-    const float w_mix = __fmul_rn(w_old, w_new);
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      if (val[k]) {
-        const size_t off = row0 + row[k] * D;
-        float mean[D], var[D];
-        load_row<D>(a.norm_mean + off, mean);
-        load_row<D>(a.norm_var + off, var);
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-          const float delta = __fsub_rn(x[k][c], mean[c]);
-          mean[c] = __fadd_rn(mean[c], __fmul_rn(delta, w_new));
-          var[c] = __fadd_rn(__fmul_rn(var[c], w_old), __fmul_rn(__fmul_rn(delta, delta), w_mix));
-          const float z = __fmul_rn(__fsub_rn(x[k][c], mean[c]), rsqrtf(__fadd_rn(var[c], a.norm_eps)));
-          x[k][c] = min_nan(max_nan(z, -a.norm_clip), a.norm_clip);
-        }
-        store_row<D>(a.norm_mean + off, mean);
-        store_row<D>(a.norm_var + off, var);
-        if (a.obs_norm != nullptr) store_row<D>(a.obs_norm + off, x[k]);
-      }
-    }
-  }
-
-  const uint32_t env_g = (uint32_t)(a.env_offset + e);
-  uint32_t drop_base = 0;
-  if (TRAIN) {
-    const unsigned long long off = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
-    drop_base = fmix32(a.seed_lo ^ fmix32(env_g * 0x9E3779B1u + (uint32_t)off) ^ (a.seed_hi * 0x85EBCA77u) ^ ((uint32_t)(off >> 32) * 0xC2B2AE3Du));
-  }
-  for (int blk = 0; blk < a.NB; ++blk) {
-    const float* __restrict__ W = wsm + blk * a.wstride;
-    uint32_t key[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) key[k] = TRAIN ? fmix32(drop_base ^ ((uint32_t)(blk * PW_MAX_S + row[k]) * 0x27D4EB2Fu)) : 0u;
-    // ---------------- set attention [rpo_transformer_agent_network.py:57-75]
-    float y[R][D];
-#pragma unroll
-    for (int k = 0; k < R; ++k)
-#pragma unroll
-      for (int c = 0; c < D; ++c) y[k][c] = W[L::BD + c];
-#pragma unroll 1
-    for (int d = 0; d < D; ++d) {
-      float2 pq[R][L::QP / 2];
-      {
-        const float4* __restrict__ bq = reinterpret_cast<const float4*>(W + L::QKV_B + d * L::QP);
-#pragma unroll
-        for (int t = 0; t < L::QP / 4; ++t) {
-          const float4 b = bq[t];
-#pragma unroll
-          for (int k = 0; k < R; ++k) { pq[k][2 * t] = lo(b); pq[k][2 * t + 1] = hi(b); }
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        const float4* __restrict__ wq = reinterpret_cast<const float4*>(W + L::QKV_W + (d * D + c) * L::QP);
-#pragma unroll
-        for (int t = 0; t < L::QP / 4; ++t) {
-          const float4 w = wq[t];
-#pragma unroll
-          for (int k = 0; k < R; ++k) {
-            pq[k][2 * t] = __ffma2_rn(splat(x[k][c]), lo(w), pq[k][2 * t]);
-            pq[k][2 * t + 1] = __ffma2_rn(splat(x[k][c]), hi(w), pq[k][2 * t + 1]);
-          }
-        }
-      }
-      auto flat = [](const float2* p, int t) { return (t & 1) ? p[t >> 1].y : p[t >> 1].x; };
-      float q[R][H];
-      float kn = 0.f, qn[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        float kn_k = 0.f;
-        qn[k] = 0.f;
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-          q[k][h] = flat(pq[k], h) * a.qscale;
-          const float kv = flat(pq[k], H + h);
-          ks[h * PW_MAX_S + row[k]] = kv;
-          vs[h * PW_MAX_S + row[k]] = flat(pq[k], 2 * H + h);
-          kn_k = fmaf(kv, kv, kn_k);
-          qn[k] = fmaf(q[k][h], q[k][h], qn[k]);
-        }
-        kn = fmaxf(kn, val[k] ? kn_k : 0.f);
-      }
-      // softmax shift: q.k_j <= |q| max_j |k_j|   (non-negative floats order like their bit patterns -> one REDUX)
-      const float kmax = sqrtf(__uint_as_float(__reduce_max_sync(hm, __float_as_uint(kn))));
-      float2 nm[R], q2[R][H], acc[P][H], l[P];
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        nm[k] = splat(-sqrtf(qn[k]) * kmax);
-#pragma unroll
-        for (int h = 0; h < H; ++h) q2[k][h] = splat(q[k][h]);
-      }
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        l[p] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int h = 0; h < H; ++h) acc[p][h] = make_float2(0.f, 0.f);
-      }
-      __syncwarp(hm);
-      int j = 0;
-      constexpr int UNR = EVAC_PWR_UNROLL;
-#pragma unroll(UNR)
-      for (; j + 4 <= S; j += 4) attn_group_rows<H, P, false>(ks, vs, j, 4, q2, nm, l, acc);
-      if (j < S) attn_group_rows<H, P, true>(ks, vs, j, S - j, q2, nm, l, acc);
-      float o[R][H];
-      bool bad = false;
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const float sum = (k & 1) ? l[k >> 1].y : l[k >> 1].x;
-        const float inv = 1.f / sum;
-#pragma unroll
-        for (int h = 0; h < H; ++h) o[k][h] = ((k & 1) ? acc[k >> 1][h].y : acc[k >> 1][h].x) * inv;
-        bad |= val[k] && !(sum >= 1e-30f && sum <= 3e38f);
-      }
-      // a bound so loose that every term underflowed (or a non-finite input): redo the row with the exact maximum
-      if (__any_sync(hm, bad)) {
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          const float sum = (k & 1) ? l[k >> 1].y : l[k >> 1].x;
-          if (val[k] && !(sum >= 1e-30f && sum <= 3e38f)) attn_row_exact<H>(ks, vs, S, q[k], o[k]);
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float* __restrict__ wd = W + L::WD + (d * H + h) * L::DP;
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-          const float w = wd[c];
-#pragma unroll
-          for (int k = 0; k < R; ++k) y[k][c] = fmaf(o[k][h], w, y[k][c]);
-        }
-      }
-      __syncwarp(hm);  // the (k, v) tile is rewritten by the next pseudo-head
-    }
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        float v = y[k][c];
-        if (TRAIN) v *= drop_mask(key[k], c, a);
-        x[k][c] = a.use_resid ? x[k][c] + v : v;
-      }
-      layer_norm<D>(x[k], W + L::LN1G, W + L::LN1B, a.ln_eps);
-    }
-
-    // ---------------- feed-forward: Linear(D, F) -> Dropout -> ReLU -> Linear(F, D), four hidden features per group
-    float2 f[R][D];
-#pragma unroll
-    for (int k = 0; k < R; ++k)
-#pragma unroll
-      for (int c = 0; c < D; ++c) f[k][c] = make_float2(0.f, 0.f);
-    const int groups = a.F4 >> 2;
-#pragma unroll 1
-    for (int g = 0; g < groups; ++g) {
-      const float4* __restrict__ G = reinterpret_cast<const float4*>(W + L::FF + g * L::GS);
-      const float4 b1 = G[0];
-      float2 h01[R], h23[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) { h01[k] = lo(b1); h23[k] = hi(b1); }
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        const float4 w = G[1 + c];
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          h01[k] = __ffma2_rn(splat(x[k][c]), lo(w), h01[k]);
-          h23[k] = __ffma2_rn(splat(x[k][c]), hi(w), h23[k]);
-        }
-      }
-      if (TRAIN) {
-        const uint32_t th = a.drop_thresh << 16;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          const uint32_t t1 = fmix32(key[k] + (8u + g) * 0x9E3779B9u);
-          uint32_t t2 = t1 * 0x9E3779B1u;
-          t2 ^= t2 >> 15;
-          if ((t1 << 16) < th) h01[k].x = 0.f;
-          if (t1 < th) h01[k].y = 0.f;
-          if ((t2 << 16) < th) h23[k].x = 0.f;
-          if (t2 < th) h23[k].y = 0.f;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        h01[k].x = max_nan(h01[k].x, 0.f); h01[k].y = max_nan(h01[k].y, 0.f);
-        h23[k].x = max_nan(h23[k].x, 0.f); h23[k].y = max_nan(h23[k].y, 0.f);
-      }
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        const float4 w = G[1 + D + c];
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          f[k][c] = __ffma2_rn(h01[k], lo(w), f[k][c]);
-          f[k][c] = __ffma2_rn(h23[k], hi(w), f[k][c]);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        float z = W[L::B2 + c] + (f[k][c].x + f[k][c].y);
-        if (TRAIN) z *= drop_mask(key[k], 8 + c, a);
-        x[k][c] = a.use_resid ? x[k][c] + z : z;
-      }
-      layer_norm<D>(x[k], W + L::LN2G, W + L::LN2B, a.ln_eps);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < R; ++k)
-    if (val[k]) store_row<D>(a.emb + row0 + row[k] * D, x[k]);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
 // critic / actor heads + sampling
 //
 // CTA = 32 environments x 128 hidden columns = one warp pair per split-K group (4 groups) (columns [0, 64) critic, [64, 128) actor; a head narrower than 64

@@ -211,6 +211,9 @@ class EvacuationEnv:
         return self
 
     def _stream(self):
+        # every library call on torch's current stream goes through here: the host face (evac_step_host, its own non-blocking
+        # stream) must wait for that work once before its next step
+        self._host_sync_needed = True
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _configure_obs(self, **kw):
@@ -533,7 +536,9 @@ class EvacuationEnv:
         # observations alias live state in the same way, env.py:100-102)
         hn = self._host_np
         obs, rew, term, trunc = hn["obs"], hn["rew"], hn["term"], hn["trunc"]
-        torch.cuda.current_stream(self.device).synchronize()
+        if getattr(self, "_host_sync_needed", True):  # only after work was queued on torch's stream (reset, set_state, ...)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._host_sync_needed = False
         pa, po, pr, pt, pu, ps = self._host_ptrs[:6]
         want_statuses = self.rng == "numpy" or E == 1  # (a large Philox batch does not pay the extra N bytes per env)
         nat.check(lib.evac_step_host(h, pa, pn, po, pr, pt, pu, ps if want_statuses else None))

@@ -574,15 +574,18 @@ int evac_step_host(EvacHandle* h, const float* actions, const float* noise, floa
   for (int i = 0; i < 7; ++i)
     if (ptrs[i] != h->pin_key[i]) { h->pin_key[i] = ptrs[i]; h->pin_val[i] = is_pinned(ptrs[i]); }
   const bool pa = h->pin_val[0], pn = h->pin_val[1], po = h->pin_val[2], pr = h->pin_val[3], pt = h->pin_val[4], pu = h->pin_val[5], ps = h->pin_val[6];
-  // Small batches (the reference-shaped single environment above all): when every caller buffer is page-locked the kernel
+  // Small batches (the reference-shaped single environment above all; up to 1 MB of inputs + results = ~680 envs x 60): when every
+  // caller buffer is page-locked the kernel
   // reads the actions / noise from and writes its results into HOST memory directly (unified addressing: a page-locked host
   // pointer is a device pointer) -- one launch + one synchronise instead of copy, launch, copy, synchronise; a few KB over PCIe
-  // cost less than the latency of two copy operations.  EVAC_HOST_ZEROCOPY=0: off (A/B).  Large batches keep the copy engine
-  // (4096 envs: the strided observation stores run at 48 GB/s against the engine's 55).
+  // cost less than the latency of two copy operations.  EVAC_HOST_ZEROCOPY=0: off, EVAC_HOST_ZEROCOPY_BYTES: the limit (A/B).  Measured
+  // per step with / without (tools/host_face_sweep.py): 21 / 27 us (1 env), 24 / 28 (32), 27 / 32 (128), 40 / 45 (512); beyond, the copy
+  // engine wins (2048 envs: 124 / 95 us, 4096: 401 / 145 -- the strided observation stores over PCIe).
   {
     static const bool zc_on = [] { const char* z = getenv("EVAC_HOST_ZEROCOPY"); return !(z && z[0] == '0'); }();
+    static const size_t zc_max = [] { const char* z = getenv("EVAC_HOST_ZEROCOPY_BYTES"); return z ? (size_t)atoll(z) : (size_t)1 << 20; }();
     const size_t bytes = E * (D * 4 + 14 + N * 5);
-    if (zc_on && bytes <= 32768 && pa && (!noise || pn) && (!obs || po) && (!reward || pr) && (!terminated || pt) && (!truncated || pu) &&
+    if (zc_on && bytes <= zc_max && pa && (!noise || pn) && (!obs || po) && (!reward || pr) && (!terminated || pt) && (!truncated || pu) &&
         (!statuses || ps)) {
       if (int r = rollout_impl(h, 1, EVAC_AGENT_TABLE, actions, noise, obs, 0, reward ? reward : h->d_reward, terminated ? terminated : h->d_term,
                                truncated ? truncated : h->d_trunc, nullptr, statuses, st)) return r;

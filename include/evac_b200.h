@@ -174,7 +174,7 @@ int evac_step(EvacHandle* h, const float* actions, const float* noise, float* ob
  *              pedestrians.py:12; the rng="numpy" face needs them to draw the next step's |viscek + follower| noise
  *              values, area.py:124).  When obs, reward, terminated, truncated, statuses are page-locked and laid out back
  *              to back in that order, the whole result travels in ONE device->host copy.  When every buffer is page-locked
- *              and the batch is small (inputs + results <= 32 KB: the single environment), nothing is copied at all: the
+ *              and the batch is small (inputs + results <= 1 MB: the single environment up to a few hundred), nothing is copied at all: the
  *              kernel reads and writes the host buffers directly (unified addressing). */
 int evac_step_host(EvacHandle* h, const float* actions, const float* noise, float* obs, float* reward,
                    uint8_t* terminated, uint8_t* truncated, uint8_t* statuses);

@@ -593,13 +593,20 @@ int evac_step_host(EvacHandle* h, const float* actions, const float* noise, floa
       return EVAC_OK;
     }
   }
-  if (!pa) memcpy(h->h_actions, actions, E * 8);
-  CK(cudaMemcpyAsync(h->d_actions, pa ? actions : h->h_actions, E * 8, cudaMemcpyHostToDevice, st));
+  // large batches: the results go through the copy engine; page-locked ACTIONS (8 bytes per environment) are still read by the kernel
+  // straight from host memory -- one copy operation less in front of the launch (EVAC_HOST_ACTIONS_ZEROCOPY=0: copy them, A/B)
+  static const bool act_zc = [] { const char* z = getenv("EVAC_HOST_ACTIONS_ZEROCOPY"); return !(z && z[0] == '0'); }();
+  const float* act_dev = h->d_actions;
+  if (pa && act_zc) act_dev = actions;
+  else {
+    if (!pa) memcpy(h->h_actions, actions, E * 8);
+    CK(cudaMemcpyAsync(h->d_actions, pa ? actions : h->h_actions, E * 8, cudaMemcpyHostToDevice, st));
+  }
   if (noise) {
     if (!pn) memcpy(h->h_noise, noise, E * N * 4);
     CK(cudaMemcpyAsync(h->d_noise, pn ? noise : h->h_noise, E * N * 4, cudaMemcpyHostToDevice, st));
   }
-  if (int r = rollout_impl(h, 1, EVAC_AGENT_TABLE, h->d_actions, noise ? h->d_noise : nullptr, obs ? h->d_obs : nullptr, 0, h->d_reward, h->d_term,
+  if (int r = rollout_impl(h, 1, EVAC_AGENT_TABLE, act_dev, noise ? h->d_noise : nullptr, obs ? h->d_obs : nullptr, 0, h->d_reward, h->d_term,
                            h->d_trunc, nullptr, statuses ? h->d_status : nullptr, st)) return r;
   const size_t head_bytes = E * D * 4 + E * 4 + 2 * E;
   const bool packed = reward == obs + E * D && terminated == (uint8_t*)(reward + E) && truncated == terminated + E &&

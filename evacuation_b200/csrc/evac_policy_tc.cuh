@@ -9,22 +9,23 @@
 // 1: actor -- the heads share nothing after the embedding) for batches that would otherwise leave SMs idle.
 //
 // Layer 1: K in chunks of 32 (one 128-byte swizzle row of float32).  float32 fidelity from kind::tf32 MMAs (10-bit mantissa
-// operands) by the 3xTF32 split:  x = xh + xl, w = wh + wl (xh / wh = the value rounded to 10 mantissa bits,
-// xl / wl = the float32 remainder, truncated by the tensor core to its top 10 bits):
+// operands) by the 3xTF32 split:  x = xh + xl, w = wh + wl (xh / wh = the 10-mantissa-bit part, xl / wl = the float32
+// remainder, of which the tensor core keeps the top 10 bits):
 //   x w  ~=  xh wh + xl wh + xh wl          (error ~2^-21 per product; the xl wl term is below float32 resolution)
 // accumulated in float32 in tensor memory.  Per chunk and CTA: 4 k-steps (UMMA_K = 8) x 3 products = 12 tcgen05.mma
-// (M = 128, N = NT) issued by ONE thread of a dedicated warp; operands in shared memory in the canonical K-major
-// SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row-in-atom) -- X arrives by cp.async straight into
-// the swizzled hi tile, two chunks ahead (the tensor core ignores the low mantissa bits itself), the four producer warps
-// only add the lo tile; the weight tiles are split and swizzled once on the host (evac_policy_load_weights) and arrive
-// as ONE bulk copy per chunk (cp.async.bulk + mbarrier complete_tx).  Ring of STAGES stages: full[s] (128 producer arrivals + the bulk copy's bytes) / empty[s] (tcgen05.commit).
+// (M = 128, N = NT) issued by ONE elected lane of a dedicated warp; operands in shared memory in the canonical K-major
+// SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row-in-atom).  X arrives by cp.async straight into
+// the swizzled hi tile, two chunks ahead (kind::tf32 ignores the low mantissa bits itself, so the raw value is xh), the eight
+// producer warps only add the lo tile; the weight tiles are split and swizzled once on the host (evac_policy_load_weights)
+// and arrive as ONE bulk copy per chunk (cp.async.bulk + mbarrier complete_tx).  Ring of STAGES stages: full[s] (256
+// producer arrivals + the bulk copy's bytes) / empty[s] (tcgen05.commit).
 //
-// Layer 2 stays on chip: epilogue 1 (tcgen05.ld 32x32b: eight warps, warp w reads TMEM lanes 32 (w % 4) .. = environments and half of
-// the columns; + bias, tanh)
-// writes H1 -- split into hi / lo again -- as the A operand tiles of the second product into the drained ring, the layer-2
-// weight tiles (32 KB per head) arrive by one more bulk copy, 24 MMAs (N = 64) per head accumulate into further TMEM
-// columns.  Epilogue 2: + bias, tanh, the (1 + A) x 64 output layer as per-thread dot products straight from the TMEM
-// loads, then the sampling tail shared with the CUDA-core kernel (heads_finish).  H1 / H2 never touch global memory.
+// Layer 2 stays on chip: epilogue 1 (tcgen05.ld 32x32b: warp w reads TMEM lanes 32 (w % 4) .. = environments and column half
+// w / 4; + bias, tanh) writes H1 -- split into hi / lo again -- as the A operand tiles of the second product into the drained
+// ring, the layer-2 weight tiles (32 KB per head) arrive by one more bulk copy, 24 MMAs (N = 64) per head accumulate into
+// further TMEM columns.  Epilogue 2: + bias, tanh, the (1 + A) x 64 output layer as per-thread dot products straight from the
+// TMEM loads (column halves combined through shared memory), then the sampling tail shared with the CUDA-core kernel
+// (heads_finish).  H1 / H2 never touch global memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

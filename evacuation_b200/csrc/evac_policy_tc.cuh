@@ -12,8 +12,8 @@
 // operands) by the 3xTF32 split:  x = xh + xl, w = wh + wl (xh / wh = the 10-mantissa-bit part, xl / wl = the float32
 // remainder, of which the tensor core keeps the top 10 bits):
 //   x w  ~=  xh wh + xl wh + xh wl          (error ~2^-21 per product; the xl wl term is below float32 resolution)
-// accumulated in float32 in tensor memory.  Per chunk and CTA: 4 k-steps (UMMA_K = 8) x 3 products = 12 tcgen05.mma
-// (M = 128, N = NT) issued by ONE elected lane of a dedicated warp; operands in shared memory in the canonical K-major
+// accumulated in float32 in tensor memory.  Per chunk and CTA: 4 k-steps (UMMA_K = 8) x 2 = 8 tcgen05.mma -- xh x [wh | wl]
+// (N = 2 NT: the hi and lo weight tiles are one B tile) and xl x wh (N = NT), M = 128 -- issued by ONE elected lane of a dedicated warp; operands in shared memory in the canonical K-major
 // SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row-in-atom).  X arrives by cp.async straight into
 // the swizzled hi tile, two chunks ahead (kind::tf32 ignores the low mantissa bits itself, so the raw value is xh), the eight
 // producer warps only add the lo tile; the weight tiles are split and swizzled once on the host (evac_policy_load_weights)
@@ -163,6 +163,8 @@ template <int NT, int ST, int AH, int MINB>
 __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(const __grid_constant__ TCArgs a) {
   using SH = TCShape<NT, ST, AH>;
   constexpr int STAGES = SH::STAGES, HEADS = SH::HEADS, TC_AHEAD = SH::AHEAD;
+  // TMEM columns: layer 1 [0, NT) = xh wh + xl wh, [NT, 2 NT) = xh wl (summed by epilogue 1); layer 2 from 2 NT; power of two
+  constexpr int TMEM_COLS = NT == 64 ? 256 : 512;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = tc_smem_raw + ((1024u - (tc_smem_u32(tc_smem_raw) & 1023u)) & 1023u);  // swizzle atoms: 1024-byte aligned (offset, so the pointer stays a shared-memory one)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * SH::STAGE_BYTES);
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EW) {  // 2 NT TMEM columns of float32 accumulators (layer 1 | layer 2), one warp allocates and later frees
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "n"(2 * NT) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = tid; i < TC_COLS; i += TC_THREADS) { b1s[i] = h.b1[i]; b2s[i] = h.b2[i]; }
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
   if (warp == TC_EW) {
     // ---- MMA issue: the whole warp follows the barriers, ONE elected lane issues (12 tcgen05.mma per chunk, stage handed back
     // through tcgen05.commit)
-    constexpr uint32_t IDESC1 = tc_idesc<NT>(), IDESC2 = tc_idesc<HD_HS>();
+    constexpr uint32_t IDESC1 = tc_idesc<NT>(), IDESC1W = tc_idesc<2 * NT>(), IDESC2 = tc_idesc<HD_HS>();
     for (int c = 0; c < a.chunks; ++c) {
       const int s = c % STAGES;
       tc_mbar_wait(&full[s], (uint32_t)((c / STAGES) & 1));
@@ -210,15 +212,15 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tc_elect()) {
         const uint32_t xh = tc_desc_lo(tc_smem_u32(smem + s * SH::STAGE_BYTES)), xl = xh + (TC_XTILE_BYTES >> 4);
-        const uint32_t wh = xh + (2 * TC_XTILE_BYTES >> 4), wl = wh + (SH::WTILE_BYTES >> 4);
-        if (c == 0) tc_mma<false>(tmem, xh, wh, IDESC1); else tc_mma<true>(tmem, xh, wh, IDESC1);
+        const uint32_t wh = xh + (2 * TC_XTILE_BYTES >> 4);   // [W hi | W lo]: 2 NT rows, the lo tile right behind the hi tile
+        // per k-step TWO MMAs: xh x [wh | wl] (the hi and lo weight tiles are one 2 NT-row B tile: N = 2 NT) and xl x wh (N = NT)
+        // -- the xh slice is read from shared memory once instead of twice (14 instead of 18 KB of operand reads per k-step)
+        if (c == 0) tc_mma<false>(tmem, xh, wh, IDESC1W); else tc_mma<true>(tmem, xh, wh, IDESC1W);
         tc_mma<true>(tmem, xl, wh, IDESC1);
-        tc_mma<true>(tmem, xh, wl, IDESC1);
 #pragma unroll
         for (int k = 1; k < TC_KC / 8; ++k) {  // UMMA_K = 8 float32 = 32 bytes along the swizzled row = + 2 in the descriptor
-          tc_mma<true>(tmem, xh + 2 * k, wh + 2 * k, IDESC1);
+          tc_mma<true>(tmem, xh + 2 * k, wh + 2 * k, IDESC1W);
           tc_mma<true>(tmem, xl + 2 * k, wh + 2 * k, IDESC1);
-          tc_mma<true>(tmem, xh + 2 * k, wl + 2 * k, IDESC1);
         }
         tc_commit(&empty[s]);
         if (c == a.chunks - 1) tc_commit(&accum[0]);
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
     if (tc_elect()) {
 #pragma unroll
       for (int hd = 0; hd < HEADS; ++hd) {
-        const uint32_t d = tmem + (uint32_t)(NT + hd * HD_HS);
+        const uint32_t d = tmem + (uint32_t)(2 * NT + hd * HD_HS);
 #pragma unroll
         for (int c = 0; c < HD_HS / TC_KC; ++c) {
           const uint32_t xh = tc_desc_lo(tc_smem_u32(a2 + (hd * (HD_HS / TC_KC) + c) * 2 * TC_XTILE_BYTES)), xl = xh + (TC_XTILE_BYTES >> 4);
@@ -308,8 +310,11 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
 #pragma unroll 1
     for (int jj = 0; jj < CW / 32; ++jj) {
       const int j = ch * (CW / 32) + jj;                        // 32-column block = k-chunk of layer 2
-      uint32_t v[32];
+      uint32_t v[32], v2[32];
       tc_tmem_ld32(trow + (uint32_t)(j * 32), v);
+      tc_tmem_ld32(trow + (uint32_t)(NT + j * 32), v2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
       uint8_t* tile = a2 + j * 2 * TC_XTILE_BYTES;
       const float* bj = b1s + y * NT + j * 32;
 #pragma unroll
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
     for (int jj = 0; jj < CW / 32; ++jj) {
       const int j = ch * (CW / 32) + jj;
       uint32_t v[32];
-      tc_tmem_ld32(trow + (uint32_t)(NT + j * 32), v);
+      tc_tmem_ld32(trow + (uint32_t)(2 * NT + j * 32), v);
       const int col0 = y * NT + j * 32;               // hidden column of v[0]: < 64 critic, >= 64 actor
       const float* bj = b2s + col0;
       if (col0 < HD_HS) {
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) evac_policy_heads_tc_kernel(
   TC_STAMP(9);
   if (warp == TC_EW) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NT) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
 }
 

@@ -532,8 +532,8 @@ def run_ours(args):
                          auto_reset=True, batched=False, rng="philox", env_index_offset=shard_offset(rank, E))
     env_h.reset()
     host_actions = actions[W:W + K].cpu().numpy()
-    for s in range(3):
-        env_h.step(host_actions[s])
+    for s in range(3):  # warm-up of the host face (K may be below 3)
+        env_h.step(host_actions[s % K])
     barrier()
     t0 = time.perf_counter()
     for s in range(K):

@@ -948,3 +948,28 @@ def test_checkpoint_resume_is_bit_identical(n, precision):
         assert torch.equal(w, g1) and torch.equal(w, g2)
     with pytest.raises(ValueError):
         b.unwrapped.load_state(image[:-16])
+
+
+@pytest.mark.parametrize("E", [1, 3, 300, 1500])
+def test_host_face_equals_the_device_face(E):
+    """`evac_step_host` (NumPy in / NumPy out) against `evac_step` (device tensors) on the same seeded batch and actions:
+    bit-identical observations, rewards and flags on every step.  E <= ~680 takes the zero-copy path (the kernel reads and
+    writes the page-locked host block), larger batches the copy engine with the actions read from host memory."""
+    import evacuation_b200 as eb
+
+    env_kw = dict(number_of_pedestrians=60, is_new_exiting_reward=True, is_new_followers_reward=True, max_timesteps=12, wandb_enabled=False)
+    wrap = dict(positions="rel", statuses="ohe", type="Box")
+    dev_env = eb.setup_env(eb.EnvConfig(**env_kw), eb.EnvWrappersConfig(**wrap), num_envs=E, batched=True, auto_reset=True, seed=11)
+    host_env = eb.setup_env(eb.EnvConfig(**env_kw), eb.EnvWrappersConfig(**wrap), num_envs=E, batched=False, auto_reset=True, seed=11,
+                            rng="philox")
+    o_d, _ = dev_env.reset()
+    o_h, _ = host_env.reset()
+    assert np.array_equal(np.asarray(o_h).reshape(E, -1), o_d.reshape(E, -1).cpu().numpy())
+    acts = np.random.RandomState(5).uniform(-1, 1, size=(30, E, 2)).astype(np.float32)
+    for t in range(30):  # crosses two truncations (same-step auto-reset) at max_timesteps = 12
+        od, rd, td, ud, _ = dev_env.step(torch.as_tensor(acts[t]))
+        oh, rh, th, uh, _ = host_env.step(acts[t] if E > 1 else acts[t, 0])
+        assert np.array_equal(np.asarray(oh).reshape(E, -1), od.reshape(E, -1).cpu().numpy()), t
+        assert np.array_equal(np.asarray(rh, dtype=np.float32).reshape(E), rd.cpu().numpy()), t
+        assert np.array_equal(np.asarray(th).reshape(E), td.cpu().numpy().astype(bool)) and np.array_equal(np.asarray(uh).reshape(E), ud.cpu().numpy().astype(bool)), t
+    assert np.asarray(uh).reshape(E).any() or t > 0
